@@ -1,0 +1,1088 @@
+/*
+ * sf_core.cuh -- the per-arena tick of the batched simulator (device code).
+ *
+ * One CUDA thread advances one arena; the 32 lanes of a warp walk the slot arrays of 32
+ * neighbouring arenas in lock step (state layout: sf_state.h).  Everything here is a
+ * from-scratch formulation of the loop body of gameplay::play()
+ * (reference StrikeForce-client/gameplay.hpp:1443-1472) on that layout; each function names
+ * the reference code whose observable behaviour it reproduces bit for bit.
+ *
+ * The file is plain C++ under SF_FN so that tests/hostcheck can compile the very same
+ * functions with g++ and diff them against the CPU models without a GPU.  That build is
+ * a debugging aid for tests only; the product library contains the CUDA build alone.
+ */
+#ifndef SF_CORE_CUH
+#define SF_CORE_CUH
+
+#include "sf_state.h"
+#include "sf_synth.h"
+
+#ifdef __CUDACC__
+#define SF_FN __device__ __forceinline__
+#define SF_MFN __device__ __forceinline__
+#define SF_UNROLL _Pragma("unroll")
+#else
+#define SF_FN static inline
+#define SF_MFN inline
+#define SF_UNROLL
+#endif
+
+#define SF_RNG_ZERO 0x10000u /* log-domain marker of the value 0 (only during the warm-up) */
+
+/* tables every lane reads: shared memory on the device, plain arrays in the host check */
+struct SfTabs {
+    const uint8_t *smap;     /* static map bytes [SF_CELLS] */
+    const uint16_t *exp_tab; /* [65536] */
+    const uint16_t *log_tab; /* [65536] */
+};
+
+/* register-resident part of one arena while a kernel works on it */
+struct SfEnv {
+    uint32_t frame, steps, episode, jomle, ntemp;
+    int32_t kills, tkills, loot, chest;
+    int32_t level, status, hw_h;
+    uint64_t mh, mz[2], mb[2], mp[2];
+    uint64_t quit;       /* humans whose Hp was zeroed by '_' (gameplay.hpp:696-699) */
+    uint32_t L[18];      /* log_3 of random[0..17] (random.hpp:31) */
+    uint32_t cst[18];    /* 2*seed[i] | 2*log_3(us[i]) << 8 */
+    uint32_t draws;      /* _rand() calls in this kernel (statistics) */
+};
+
+/* ------------------------------------------------------------------ small helpers */
+
+SF_FN int sf_ffs64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)x) - 1;
+#else
+    return x ? __builtin_ctzll(x) : -1;
+#endif
+}
+SF_FN int sf_fls64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return 63 - __clzll((long long)x);
+#else
+    return x ? 63 - __builtin_clzll(x) : -1;
+#endif
+}
+SF_FN int sf_popc64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+/* 128-bit slot masks as two words */
+SF_FN bool m2_test(const uint64_t m[2], int i) { return (m[i >> 6] >> (i & 63)) & 1; }
+SF_FN void m2_set(uint64_t m[2], int i) { m[i >> 6] |= 1ull << (i & 63); }
+SF_FN void m2_clear(uint64_t m[2], int i) { m[i >> 6] &= ~(1ull << (i & 63)); }
+SF_FN int m2_lowest_free(const uint64_t m[2])
+{
+    if (~m[0]) return sf_ffs64(~m[0]);
+    if (~m[1]) return 64 + sf_ffs64(~m[1]);
+    return 128;
+}
+SF_FN int m2_highest(const uint64_t m[2])
+{
+    if (m[1]) return 64 + sf_fls64(m[1]);
+    return sf_fls64(m[0]);
+}
+SF_FN int m2_count(const uint64_t m[2]) { return sf_popc64(m[0]) + sf_popc64(m[1]); }
+/* next set bit at or above i (ascending walk), -1 if none */
+SF_FN int m2_next(const uint64_t m[2], int i)
+{
+    if (i < 64) {
+        uint64_t w = m[0] >> i;
+        if (w) return i + sf_ffs64(w);
+        i = 64;
+    }
+    if (i < 128) {
+        uint64_t w = m[1] >> (i - 64);
+        if (w) return i + sf_ffs64(w);
+    }
+    return -1;
+}
+/* next set bit at or below i (descending walk), -1 if none */
+SF_FN int m2_prev(const uint64_t m[2], int i)
+{
+    if (i >= 64) {
+        uint64_t w = m[1] << (127 - i);
+        if (w) return i - (63 - sf_fls64(w));
+        i = 63;
+    }
+    if (i >= 0) {
+        uint64_t w = m[0] << (63 - i);
+        if (w) return i - (63 - sf_fls64(w));
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ addressing */
+
+#define SF_AT(arr, slot) (arr)[(size_t)(slot) * (size_t)d.E + (size_t)env]
+#define SF_G(cell) d.grid[(size_t)env * SF_GRID_STRIDE + (size_t)(cell)]
+
+SF_FN int sf_cell_of(int f, int r, int c) { return (f * SF_ROWS + r) * SF_COLS + c; }
+SF_FN int sf_row_of(int cell) { return (cell / SF_COLS) % SF_ROWS; }
+SF_FN int sf_col_of(int cell) { return cell % SF_COLS; }
+/* wdx / wdy, gameplay.hpp:459: way-1 = 0 down(+row) 1 right(+col) 2 up 3 left */
+SF_FN int sf_delta(int d) { return d == 0 ? SF_COLS : d == 1 ? 1 : d == 2 ? -SF_COLS : -1; }
+/* neighbour in direction d with the bounds test obey() makes (gameplay.hpp:704, 747, 801) */
+SF_FN bool sf_neighbour(int cell, int d, int *out)
+{
+    int r = sf_row_of(cell), c = sf_col_of(cell);
+    r += (d == 0) - (d == 2);
+    c += (d == 1) - (d == 3);
+    *out = cell + sf_delta(d);
+    return !(r >= SF_ROWS || r < 0 || c >= SF_COLS || c < 0);
+}
+
+/* node::showit(), gameplay.hpp:321-341, from the static byte and the overlay word.  s[8]
+ * (death mark) is render-only: updmap() clears it before any rule reads a cell (:489-495). */
+SF_FN int sf_showit(uint32_t st, uint32_t g)
+{
+    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+    if ((st & M_WALL) || kind == K_BLOCK) return SH_WALL;
+    if (g & C_S0) return SH_HUMAN;
+    if (g & C_S1) return SH_ZOMBIE;
+    if ((st & M_UP) || kind == K_ENTRANCE) return SH_UP;
+    if (st & M_DOWN) return SH_DOWN;
+    if (g & C_S2) return SH_BULLET;
+    if (kind >= K_CHEST0 && kind < K_BLOCK) return SH_CHEST;
+    if ((st & M_EXIT) || kind == K_EXIT) return SH_EXIT;
+    return SH_DOT;
+}
+
+/* ------------------------------------------------------------------ random.hpp */
+
+/* _rand(), random.hpp:54-62, in the discrete-log domain of the cyclic group mod 65537
+ * (generator 3).  random[i]^seed[i] * us[i] = 3^(L[i]*seed[i] + log us[i]); the new element
+ * (sum)^jomle = 3^(log(sum) * jomle).  exp_tab holds 3^k - 1, so the reference's
+ * "1 + sum of 18 terms" is 19 + sum of 18 table entries.  WARM handles the all-zero start of
+ * _srand (:64-76), where 0^seed = 0 contributes nothing. */
+template <bool WARM>
+SF_FN int sf_rand_t(SfEnv &e, const SfTabs &t)
+{
+    uint32_t S = WARM ? 1u : 19u;
+    const uint8_t *ebytes = (const uint8_t *)t.exp_tab;
+SF_UNROLL
+    for (int i = 0; i < 18; ++i) {
+        uint32_t c = e.cst[i];
+        uint32_t off = (e.L[i] * (c & 0xFFu) + (c >> 8)) & 0x1FFFEu;
+        uint32_t v = *(const uint16_t *)(ebytes + off);
+        if (WARM) S += (e.L[i] == SF_RNG_ZERO) ? 0u : v + 1u;
+        else S += v;
+    }
+    int32_t r = (int32_t)(S & 0xFFFFu) - (int32_t)(S >> 16); /* 65536 == -1 (mod 65537) */
+    if (r < 0) r += 65537;
+    if (r == 0) r = 1;                                        /* sum + (sum == 0) */
+    uint32_t lg = t.log_tab[r - 1];
+    e.jomle += 1;
+    uint32_t ln = (lg * (e.jomle & 0xFFFFu)) & 0xFFFFu;       /* binpow(sum, jomle), :42-52 */
+SF_UNROLL
+    for (int i = 0; i < 17; ++i) e.L[i] = e.L[i + 1];
+    e.L[17] = ln;
+    e.draws += 1;
+    return (int)(((uint32_t)t.exp_tab[ln] + 1u) & 1023u);
+}
+SF_FN int sf_rand(SfEnv &e, const SfTabs &t) { return sf_rand_t<false>(e, t); }
+
+/* _srand(tb, u_s), random.hpp:64-76 */
+SF_FN void sf_srand(SfEnv &e, const SfTabs &t, int64_t tb, int64_t u_s)
+{
+SF_UNROLL
+    for (int i = 0; i < 18; ++i) {
+        uint32_t us = (uint32_t)(u_s % 10 + 1), sd = (uint32_t)(tb % 10 + 1);
+        u_s /= 10;
+        tb /= 10;
+        e.cst[i] = (2u * sd) | ((2u * (uint32_t)t.log_tab[us - 1]) << 8);
+        e.L[i] = SF_RNG_ZERO;
+    }
+    e.jomle = 18;
+    for (int i = 0; i < 18; ++i) sf_rand_t<true>(e, t);
+    for (int i = 18; i < 1024; ++i) sf_rand_t<false>(e, t);
+}
+
+/* ------------------------------------------------------------------ entities */
+
+SF_FN const SfTemplate &sf_tmpl(const SfConst &k, int h) { return h == 0 ? k.player : k.npc; }
+SF_FN int sf_punch_base(const SfConst &k, const SfEnv &e, int h)
+{
+    return h == 0 ? k.player_punch_base : k.npc_punch_base[e.level];
+}
+
+/* write every field of human slot h: Human::build + gen_human (Character.hpp:650-709, 873-888)
+ * or the `hum[ind] = me` copy of load_data (gameplay.hpp:1864, 1909) */
+SF_FN void sf_init_human(const SfDev &d, int env, const SfTemplate &tp, int h, int cell, bool rnpc, int team,
+                         bool agent)
+{
+    SF_AT(d.h_pw, h) = (uint16_t)cell; /* way = 1 */
+    SF_AT(d.h_sel, h) = (uint16_t)((uint32_t)team | (rnpc ? HS_RNPC : 0u) | (agent ? HS_AGENT : 0u));
+    SF_AT(d.h_bp, h) = (uint32_t)tp.blocks | ((uint32_t)tp.portals << 8);
+    SF_AT(d.h_hp, h) = tp.hp;
+    SF_AT(d.h_mind, h) = tp.mindamage;
+    SF_AT(d.h_stam, h) = tp.stamina;
+    SF_AT(d.h_kills, h) = 0;
+    SF_AT(d.h_dmg, h) = 0;
+    SF_AT(d.h_eff, h) = 0;
+    SF_AT(d.h_cons, h) = tp.cons_packed;
+    SF_AT(d.h_thr, h) = tp.thr_packed;
+}
+
+/* lowest free bullet slot (b_ind, gameplay.hpp:230-235); a slot at or beyond the configured
+ * capacity is the harness's SF_OVERFLOW */
+SF_FN int sf_alloc_bullet(const SfConst &k, SfEnv &e)
+{
+    int b = m2_lowest_free(e.mb);
+    if (b >= k.cap_b) {
+        e.status = SF_OVERFLOW;
+        return -1;
+    }
+    m2_set(e.mb, b);
+    return b;
+}
+
+/* a new bullet becomes the cell's last writer (node::bullet under s[2]); any older owner of
+ * the same cell keeps flying but loses the flag */
+SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, uint32_t g, int way0, int range,
+                           int owner, int dmg, int eff)
+{
+    if (g & C_S2) {
+        for (int o = m2_next(e.mb, 0); o >= 0; o = m2_next(e.mb, o + 1)) {
+            if (o == b) continue;
+            uint32_t m = SF_AT(d.b_meta, o);
+            if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) {
+                SF_AT(d.b_meta, o) = m & ~BF_OWNS;
+                break;
+            }
+        }
+    }
+    SF_AT(d.b_pw, b) = (uint16_t)(cell | (way0 << POS_HI_SHIFT));
+    SF_AT(d.b_meta, b) = (uint32_t)range | ((uint32_t)(owner + 1) << 16) | BF_OWNS;
+    SF_AT(d.b_dmg, b) = dmg;
+    SF_AT(d.b_eff, b) = eff;
+    SF_G(cell) = (uint16_t)(g | C_S2);
+}
+
+/* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469) */
+SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
+{
+    for (uint32_t q = 0; q < e.ntemp; ++q)
+        if (SF_AT(d.t_cell, q) == cell) return (int)q;
+    return -1;
+}
+SF_FN void sf_remove_built(const SfDev &d, int env, SfEnv &e, int q)
+{
+    uint32_t last = e.ntemp - 1;
+    if ((uint32_t)q != last) {
+        SF_AT(d.t_cell, q) = SF_AT(d.t_cell, last);
+        SF_AT(d.t_dmg, q) = SF_AT(d.t_dmg, last);
+        SF_AT(d.t_pidx, q) = SF_AT(d.t_pidx, last);
+    }
+    e.ntemp = last;
+}
+SF_FN bool sf_push_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, int cell, int pidx)
+{
+    if ((int)e.ntemp >= k.cap_t) { /* harness: temp.size() > cap is SF_OVERFLOW */
+        e.status = SF_OVERFLOW;
+        return false;
+    }
+    SF_AT(d.t_cell, e.ntemp) = (uint16_t)cell;
+    SF_AT(d.t_dmg, e.ntemp) = 0;
+    SF_AT(d.t_pidx, e.ntemp) = (uint8_t)pidx;
+    e.ntemp += 1;
+    return true;
+}
+
+SF_FN int sf_exit_cell(const SfDev &d, const SfConst &k, int env, int idx)
+{
+    return idx < k.n_static_exits ? (int)k.static_exit_cell[idx] : (int)SF_AT(d.p_cell, idx);
+}
+
+/* ------------------------------------------------------------------ spawns */
+
+/* spawn_chest, gameplay.hpp:532-542 */
+SF_FN void sf_spawn_chest(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    if (9000 <= e.chest) return; /* C, gameplay.hpp:37 */
+    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
+    int cell = sf_cell_of(i, j, c);
+    uint32_t g = SF_G(cell);
+    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
+    int type = sf_rand(e, t) % 4;
+    SF_G(cell) = (uint16_t)((K_CHEST0 + type) << C_KIND_SHIFT);
+    e.chest += 1;
+    if (e.chest > k.cap_chest) e.status = SF_OVERFLOW;
+}
+
+/* spawn_zombie_npc, gameplay.hpp:544-557 with Zombie::gen_npc, Character.hpp:850-857 */
+SF_FN void sf_spawn_zombie(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
+    int cell = sf_cell_of(i, j, c);
+    uint32_t g = SF_G(cell);
+    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
+    int z = m2_lowest_free(e.mz);
+    if (z >= k.cap_z) {
+        e.status = SF_OVERFLOW;
+        return;
+    }
+    int super_ = (sf_rand(e, t) % 4 == 0);
+    SF_AT(d.z_pos, z) = (uint16_t)(cell | (super_ << POS_HI_SHIFT));
+    SF_AT(d.z_hp, z) = (super_ + 1) * 400;
+    SF_AT(d.z_mind, z) = (super_ + 1) * 100;
+    SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
+    m2_set(e.mz, z);
+}
+
+/* spawn_human_npc, gameplay.hpp:559-572 */
+SF_FN void sf_spawn_human(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
+    int cell = sf_cell_of(i, j, c);
+    uint32_t g = SF_G(cell);
+    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
+    int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
+    if (h < 0 || h >= k.cap_h) {
+        e.status = SF_OVERFLOW;
+        return;
+    }
+    sf_init_human(d, env, k.npc, h, cell, true, 0, false);
+    SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)h);
+    e.mh |= 1ull << h;
+    if (h + 1 > e.hw_h) e.hw_h = h + 1;
+}
+
+/* ------------------------------------------------------------------ half-tick pieces */
+
+/* zombie_action, gameplay.hpp:654-693 */
+SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    int hi = m2_highest(e.mz);
+    for (int z = 0; z <= hi; ++z) {
+        if (!m2_test(e.mz, z)) continue;
+        uint32_t pw = SF_AT(d.z_pos, z);
+        int cell = (int)(pw & POS_CELL);
+        uint32_t g = SF_G(cell);
+        if (g & C_S2) continue;
+        bool adjacent = false;
+SF_UNROLL
+        for (int i1 = 0; i1 < 4; ++i1) {
+            int nc = cell + sf_delta(i1);
+            uint32_t gn = SF_G(nc);
+            if (gn & C_S0) {
+                if (!(gn & C_S2)) {
+                    int b = sf_alloc_bullet(k, e);
+                    if (b < 0) return;
+                    int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
+                    sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+                }
+                adjacent = true;
+            }
+        }
+        if (adjacent) continue;
+        if (sf_rand(e, t) % 5 < 2) continue;
+        for (int i1 = 0; i1 < 2; ++i1) {
+            int i2 = sf_rand(e, t) % 4;
+            int nc = cell + sf_delta(i2);
+            uint32_t gn = SF_G(nc);
+            if (sf_showit(t.smap[nc], gn) == SH_DOT) {
+                SF_G(nc) = (uint16_t)(C_S1 | (uint32_t)z);
+                SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
+                SF_AT(d.z_pos, z) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
+                break;
+            }
+        }
+    }
+}
+
+/* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates */
+SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
+{
+    for (int i = m2_next(e.mp, 0); i >= 0; i = m2_next(e.mp, i + 1)) {
+        int cell = sf_exit_cell(d, k, env, i);
+        uint32_t g = SF_G(cell);
+        if (g & (C_S0 | C_S1 | C_S2)) {
+            int b = sf_alloc_bullet(k, e);
+            if (b < 0) return;
+            sf_place_bullet(d, env, e, b, cell, g, 2, 1, -1, 20, -10);
+        }
+    }
+}
+
+/* destroy test of one player-built cell, second loop of update_tmp, gameplay.hpp:1356-1373 */
+SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, int cell)
+{
+    int q = sf_find_built(d, env, e, cell);
+    if (q < 0) return;
+    uint32_t g = SF_G(cell);
+    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+    int dmg = SF_AT(d.t_dmg, q);
+    if (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)) && dmg >= 1000) { /* lim_portal */
+        int pi = SF_AT(d.t_pidx, q);
+        int ecell = sf_exit_cell(d, k, env, pi);
+        SF_G(ecell) = (uint16_t)(SF_G(ecell) & ~C_KIND);
+        SF_G(cell) = (uint16_t)(g & ~C_KIND);
+        m2_clear(e.mp, pi);
+        sf_remove_built(d, env, e, q);
+        int q1 = sf_find_built(d, env, e, ecell);
+        if (q1 >= 0) sf_remove_built(d, env, e, q1);
+    } else if (kind == K_BLOCK && dmg >= 1100) { /* lim_block */
+        SF_G(cell) = (uint16_t)(g & ~C_KIND);
+        sf_remove_built(d, env, e, q);
+    }
+}
+
+/* update_tmp, gameplay.hpp:1343-1381 */
+SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
+{
+    if (e.ntemp == 0) return; /* nothing player-built: no bullet can be absorbed */
+    int hit_cell[4];
+    int n_hit = 0;
+    bool many = false;
+    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
+        int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
+        uint32_t g = SF_G(cell);
+        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+        if (kind == K_BLOCK || (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)))) {
+            int q = sf_find_built(d, env, e, cell);
+            SF_AT(d.t_dmg, q) += SF_AT(d.b_dmg, b);
+            SF_G(cell) = (uint16_t)(g & ~C_S2);
+            m2_clear(e.mb, b);
+            if (n_hit < 4) hit_cell[n_hit++] = cell;
+            else many = true;
+        }
+    }
+    /* a limit can only be crossed by an absorption of this very call (while a human hides an
+     * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
+    if (many) {
+        for (int q = (int)e.ntemp - 1; q >= 0; --q) {
+            if (q >= (int)e.ntemp) continue;
+            sf_check_built(d, k, env, e, SF_AT(d.t_cell, q));
+        }
+    } else {
+        for (int i = 0; i < n_hit; ++i) sf_check_built(d, k, env, e, hit_cell[i]);
+    }
+}
+
+/* human_damage, gameplay.hpp:611-634 */
+SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int cell, uint32_t g, uint32_t meta)
+{
+    int dmg = SF_AT(d.b_dmg, b), eff = SF_AT(d.b_eff, b);
+    int owner = (int)((meta >> 16) & 0xFFu) - 1;
+    int hp = SF_AT(d.h_hp, h) - dmg; /* Character::hit, Character.hpp:242-246 */
+    SF_AT(d.h_hp, h) = hp;
+    SF_AT(d.h_mind, h) += eff;
+    g &= ~C_S2;
+    m2_clear(e.mb, b);
+    uint32_t team_h = SF_AT(d.h_sel, h) & HS_TEAM;
+    uint32_t team_o = owner >= 0 ? (SF_AT(d.h_sel, owner) & HS_TEAM) : 0u;
+    uint32_t team_me = SF_AT(d.h_sel, 0) & HS_TEAM;
+    if (owner >= 0 && team_h != team_o) {
+        SF_AT(d.h_dmg, owner) += dmg;
+        SF_AT(d.h_eff, owner) += eff;
+    }
+    if (hp <= 0) {
+        e.mh &= ~(1ull << h);
+        if (h != 0) {
+            g &= ~(C_S0 | C_OCC);
+            SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT); /* deleteAgent, :648-649 */
+        }
+        if (owner >= 0 && team_o == team_me && team_h != team_me) {
+            e.tkills += 1, e.loot += 100;
+            if (owner == 0) e.loot += 900, e.kills += 1;
+        }
+        if (owner >= 0 && team_h != team_o) SF_AT(d.h_kills, owner) += 1;
+    }
+    SF_G(cell) = (uint16_t)g;
+}
+
+/* zombie_damage, gameplay.hpp:574-598 */
+SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int cell, uint32_t g, uint32_t meta)
+{
+    int dmg = SF_AT(d.b_dmg, b), eff = SF_AT(d.b_eff, b);
+    int owner = (int)((meta >> 16) & 0xFFu) - 1;
+    int hp = SF_AT(d.z_hp, z) - dmg;
+    SF_AT(d.z_hp, z) = hp;
+    SF_AT(d.z_mind, z) += eff;
+    g &= ~C_S2;
+    m2_clear(e.mb, b);
+    if (owner >= 0) {
+        SF_AT(d.h_dmg, owner) += dmg;
+        SF_AT(d.h_eff, owner) += eff;
+    }
+    if (hp <= 0) {
+        m2_clear(e.mz, z);
+        g &= ~(C_S1 | C_OCC);
+        if (owner >= 0 && (SF_AT(d.h_sel, owner) & HS_TEAM) == (SF_AT(d.h_sel, 0) & HS_TEAM)) {
+            int pts = 500 + 250 * (int)(SF_AT(d.z_pos, z) >> POS_HI_SHIFT);
+            e.tkills += 1, e.loot += pts / 10;
+            if (owner == 0) e.loot += pts * 9 / 10, e.kills += 1;
+        }
+        if (owner >= 0) SF_AT(d.h_kills, owner) += 1;
+    }
+    SF_G(cell) = (uint16_t)g;
+}
+
+/* hit_human + hit_zombie, gameplay.hpp:600-609, 636-652.  The reference walks every live
+ * human / zombie and tests s[2] of its cell; a set s[2] always has exactly one owning
+ * bullet, so walking the owning bullets and looking at who stands in their cell visits the
+ * same (victim, bullet) pairs.  The pairs are independent (distinct victims, distinct
+ * bullets, credits are sums), so their order does not matter. */
+SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
+{
+    uint64_t q = e.quit & e.mh; /* first branch of hit_human: Hp <= 0 without a bullet test */
+    e.quit = 0;
+    while (q) {
+        int h = sf_ffs64(q);
+        q &= q - 1;
+        e.mh &= ~(1ull << h);
+        if (h != 0) {
+            int cell = (int)(SF_AT(d.h_pw, h) & POS_CELL);
+            SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
+            SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT);
+        }
+    }
+    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
+        uint32_t meta = SF_AT(d.b_meta, b);
+        if (!(meta & BF_OWNS)) continue;
+        int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
+        uint32_t g = SF_G(cell);
+        if (g & C_S0) {
+            int h = (int)(g & C_OCC);
+            if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b, cell, g, meta);
+        } else if (g & C_S1) {
+            sf_zombie_damage(d, env, e, (int)(g & C_OCC), b, cell, g, meta);
+        }
+    }
+}
+
+/* update_bull, gameplay.hpp:1059-1100, plus the harness's out-of-bounds guard.  Pass 1 is the
+ * themap1 snapshot with s[2] cleared on the current and next cell of every live bullet; pass 2
+ * walks the bullets in the REVERSE of the reference's order so that the first bullet to reach
+ * a cell here is the reference's last writer of it. */
+SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
+{
+    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
+        uint32_t pw = SF_AT(d.b_pw, b);
+        int cell = (int)(pw & POS_CELL), nc;
+        if (!sf_neighbour(cell, (int)(pw >> POS_HI_SHIFT), &nc)) {
+            e.status = SF_UB_GUARD; /* the reference would read themap[i][-1][k], :1069 */
+            return;
+        }
+    }
+    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
+        uint32_t pw = SF_AT(d.b_pw, b);
+        int cell = (int)(pw & POS_CELL);
+        int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
+        uint32_t g = SF_G(cell);
+        if (g & C_S2) SF_G(cell) = (uint16_t)(g & ~C_S2);
+        uint32_t gn = SF_G(nc);
+        if (gn & C_S2) SF_G(nc) = (uint16_t)(gn & ~C_S2);
+    }
+    int r = sf_rand(e, t) & 1;
+    /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
+    int b = r ? m2_prev(e.mb, 127) : m2_next(e.mb, 0);
+    while (b >= 0) {
+        uint32_t pw = SF_AT(d.b_pw, b);
+        uint32_t meta = SF_AT(d.b_meta, b) & ~BF_OWNS;
+        int cell = (int)(pw & POS_CELL);
+        uint32_t range = meta & 0xFFu, trav = (meta >> 8) & 0xFFu;
+        if (trav + 1 >= range) { /* Bullet::expire, Item.hpp:165-168 */
+            m2_clear(e.mb, b);
+        } else {
+            int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
+            uint32_t gn = SF_G(nc);
+            int sit = sf_showit(t.smap[nc], gn);
+            bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
+            if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
+                if (!(gn & C_S2)) meta |= BF_OWNS;
+                SF_G(nc) = (uint16_t)(gn | C_S2);
+                SF_AT(d.b_pw, b) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
+                SF_AT(d.b_meta, b) = meta + 0x100u;
+            } else {
+                m2_clear(e.mb, b);
+            }
+        }
+        b = r ? m2_prev(e.mb, b - 1) : m2_next(e.mb, b + 1);
+    }
+}
+
+/* human_rnpc_bot, gameplay.hpp:1927-1940; returns the command symbol */
+SF_FN int sf_rnpc_bot(const SfTabs &t, SfEnv &e)
+{
+    if (e.frame % 50 <= 1) {
+        const char c[8] = {'c', 'v', 'b', 'n', 'm', ',', '.', '/'};
+        return c[sf_rand(e, t) % 8];
+    }
+    if (sf_rand(e, t) % 5 < 3) return 'x';
+    if (sf_rand(e, t) % 5 < 3) {
+        const char c[7] = {'1', '2', 'a', 'w', 's', 'd', 'p'};
+        return c[sf_rand(e, t) % 7];
+    }
+    const char c[8] = {'+', 'u', 'f', 'g', 'h', 'j', '[', ']'};
+    return c[sf_rand(e, t) % 8];
+}
+
+/* index of a selection key in its row, -1 if c is not in it (obey, gameplay.hpp:759-791) */
+SF_FN int sf_key_index(int c, int group)
+{
+    if (group == 0) return c == 'f' ? 0 : c == 'g' ? 1 : c == 'h' ? 2 : c == 'j' ? 3 : -1;
+    if (group == 1) return c == 'k' ? 0 : c == 'l' ? 1 : c == ';' ? 2 : c == '\'' ? 3 : -1;
+    return c == 'c' ? 0 : c == 'v' ? 1 : c == 'b' ? 2 : c == 'n' ? 3 : c == 'm' ? 4 : c == ',' ? 5
+         : c == '.' ? 6 : c == '/' ? 7 : -1;
+}
+
+/* obey + teleport + claim_chest for one human, gameplay.hpp:695-821, 517-530, 507-515 */
+SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c)
+{
+    uint32_t pw = SF_AT(d.h_pw, h);
+    int cell = (int)(pw & POS_CELL);
+    int way0 = (int)(pw >> POS_HI_SHIFT);
+    if (c == '_') {
+        SF_AT(d.h_hp, h) = 0;
+        e.quit |= 1ull << h;
+    } else if (c == '[' || c == ']') {
+        int nc;
+        if (sf_neighbour(cell, way0, &nc)) {
+            uint32_t gn = SF_G(nc);
+            if (sf_showit(t.smap[nc], gn) == SH_DOT) {
+                uint32_t bp = SF_AT(d.h_bp, h);
+                uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
+                if (c == '[') {
+                    if (blocks) {
+                        if (!sf_push_built(d, k, env, e, nc, 0)) return;
+                        SF_G(nc) = (uint16_t)(K_BLOCK << C_KIND_SHIFT);
+                        SF_AT(d.h_bp, h) = bp - 1u;
+                    }
+                } else if (pend) { /* second press: the entrance bound to the pending exit */
+                    if (!sf_push_built(d, k, env, e, nc, (int)pend - 1)) return;
+                    SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
+                    SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
+                } else if (portals) { /* first press: the exit, lowest free portal slot (p_ind) */
+                    int pi = m2_lowest_free(e.mp);
+                    if (pi >= k.cap_p) {
+                        e.status = SF_OVERFLOW;
+                        return;
+                    }
+                    if (!sf_push_built(d, k, env, e, nc, 0)) return;
+                    SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
+                    SF_AT(d.p_cell, pi) = (uint16_t)nc;
+                    m2_set(e.mp, pi);
+                    SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);
+                }
+            }
+        }
+    } else if (c == 'q' || c == 'e') { /* turn_l: way+1, turn_r: way-1, Character.hpp:745-759 */
+        way0 = (c == 'e') ? ((way0 + 3) & 3) : ((way0 + 1) & 3);
+        pw = (uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT);
+        SF_AT(d.h_pw, h) = (uint16_t)pw;
+    } else if (c == 'a' || c == 's' || c == 'd' || c == 'w') {
+        int dir = c == 's' ? 0 : c == 'd' ? 1 : c == 'w' ? 2 : 3;
+        int nc;
+        if (sf_neighbour(cell, dir, &nc)) {
+            uint32_t gn = SF_G(nc);
+            int sit = sf_showit(t.smap[nc], gn);
+            if (sit == SH_CHEST || sit == SH_UP || sit == SH_DOWN || sit == SH_DOT || sit == SH_BULLET) {
+                SF_G(nc) = (uint16_t)((gn & ~C_OCC) | C_S0 | (uint32_t)h);
+                SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
+                cell = nc;
+                pw = (uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT);
+                SF_AT(d.h_pw, h) = (uint16_t)pw;
+            }
+        }
+    } else if (c == 'u') { /* Human::use, Character.hpp:379-389 */
+        uint32_t sel = SF_AT(d.h_sel, h);
+        int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
+        if (vec == 0) {
+            uint32_t cp = SF_AT(d.h_cons, h);
+            uint32_t cnt = (cp >> (8 * ind)) & 0xFFu;
+            if (cnt >= 1) {
+                SF_AT(d.h_stam, h) += k.cons[ind].stamina;
+                SF_AT(d.h_hp, h) += k.cons[ind].hp;
+                SF_AT(d.h_mind, h) += k.cons[ind].effect;
+                SF_AT(d.h_cons, h) = cp - (1u << (8 * ind));
+                if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT)); /* vec = -1 */
+            }
+        }
+    } else if (c == 'z' || c == 'x') {
+        int nc;
+        int b = m2_lowest_free(e.mb); /* b_ind() comes first, :800 */
+        if (sf_neighbour(cell, way0, &nc)) {
+            uint32_t sel = SF_AT(d.h_sel, h);
+            int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
+            bool can = false, fire = true;
+            int dmg = 0, eff = 0, range = 1;
+            if (c == 'z') { /* Human::punch, Character.hpp:391-397 */
+                int md = SF_AT(d.h_mind, h), pb = sf_punch_base(k, e, h);
+                dmg = pb > md ? pb : md;
+                can = true;
+            } else if (vec == 1) { /* Human::throw_it, Character.hpp:410-427 */
+                const SfWpn w = sf_tmpl(k, h).thr[ind];
+                int md = SF_AT(d.h_mind, h), st = SF_AT(d.h_stam, h);
+                dmg = w.damage > w.damage + md ? w.damage : w.damage + md;
+                eff = w.effect, range = w.range;
+                if (st + w.stamina >= 0) {
+                    uint32_t tp = SF_AT(d.h_thr, h);
+                    uint32_t cnt = (tp >> (8 * ind)) & 0xFFu;
+                    if (cnt < 1) {
+                        SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT));
+                    } else {
+                        SF_AT(d.h_stam, h) = st + w.stamina;
+                        SF_AT(d.h_thr, h) = tp - (1u << (8 * ind));
+                        if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT));
+                        can = true;
+                    }
+                }
+            } else if (vec == 2) { /* Human::shot_it, Character.hpp:399-408 */
+                const SfTemplate &tp = sf_tmpl(k, h);
+                const SfWpn w = tp.wpn[ind];
+                int st = SF_AT(d.h_stam, h);
+                if (st + w.stamina >= 0) {
+                    int md = SF_AT(d.h_mind, h), sb = tp.shot_base[ind];
+                    SF_AT(d.h_stam, h) = st + w.stamina;
+                    dmg = sb > w.damage + md ? sb : w.damage + md;
+                    eff = w.effect, range = w.range;
+                    can = true;
+                }
+            } else
+                fire = false;
+            if (fire && can) {
+                uint32_t gn = SF_G(nc);
+                int sit = sf_showit(t.smap[nc], gn);
+                bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
+                if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
+                    if (b >= k.cap_b) {
+                        e.status = SF_OVERFLOW;
+                        return;
+                    }
+                    m2_set(e.mb, b);
+                    sf_place_bullet(d, env, e, b, nc, gn, way0, range, h, dmg, eff);
+                }
+            }
+        }
+    } else {
+        int i;
+        if ((i = sf_key_index(c, 0)) >= 0) {
+            if ((SF_AT(d.h_cons, h) >> (8 * i)) & 0xFFu) {
+                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel | (1u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+            }
+        } else if ((i = sf_key_index(c, 1)) >= 0) {
+            if ((SF_AT(d.h_thr, h) >> (8 * i)) & 0xFFu) {
+                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel | (2u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+            }
+        } else if ((i = sf_key_index(c, 2)) >= 0) {
+            if ((sf_tmpl(k, h).w_owned >> i) & 1u) {
+                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel | (3u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+            }
+        }
+    }
+    if (e.status != SF_RUNNING) return;
+    /* teleport, gameplay.hpp:517-530 */
+    uint32_t g = SF_G(cell);
+    uint32_t st = t.smap[cell];
+    int pidx = -1;
+    if (st & (M_UP | M_DOWN)) pidx = (int)(st >> M_TARGET_SHIFT);
+    else if (((g >> C_KIND_SHIFT) & 7u) == K_ENTRANCE) pidx = SF_AT(d.t_pidx, sf_find_built(d, env, e, cell));
+    if (pidx >= 0) {
+        int dc = sf_exit_cell(d, k, env, pidx);
+        uint32_t gd = SF_G(dc);
+        if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
+            SF_G(dc) = (uint16_t)((gd & ~C_OCC) | C_S0 | (uint32_t)h);
+            SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
+            cell = dc;
+            SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
+            g = SF_G(cell);
+        }
+    }
+    /* claim_chest, gameplay.hpp:507-515, Human::claim_chest Character.hpp:372-377 */
+    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+    if (kind >= K_CHEST0 && kind < K_BLOCK) {
+        int ty = (int)kind - K_CHEST0;
+        SF_AT(d.h_stam, h) += k.cons[ty].stamina;
+        SF_AT(d.h_hp, h) += k.cons[ty].hp;
+        SF_AT(d.h_mind, h) += k.cons[ty].effect;
+        SF_G(cell) = (uint16_t)(g & ~C_KIND);
+        e.chest -= 1;
+    }
+}
+
+/* human_action, gameplay.hpp:965-1012.  actions = this arena's row of the action buffer:
+ * [0] the player's command (get_my_action, :939-963), [1..] what bot() returns for the
+ * agent-driven squad humans (bots/bot-0.5/Custom.hpp:137-158, one of "+xzqeawsd"). */
+SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e,
+                           const uint8_t *actions)
+{
+    uint8_t cmd[SF_LIM_HUMANS];
+    uint64_t live = e.mh;
+    cmd[0] = actions ? actions[0] : (uint8_t)'+';
+    for (uint64_t m = live & ~1ull; m; m &= m - 1) {
+        int h = sf_ffs64(m);
+        uint32_t sel = SF_AT(d.h_sel, h);
+        int c = '+';
+        if (sel & HS_RNPC) c = sf_rnpc_bot(t, e);
+        else if ((sel & HS_AGENT) && h < k.n_agents && actions) {
+            c = actions[h];
+            bool ok = c == '+' || c == 'x' || c == 'z' || c == 'q' || c == 'e' || c == 'a' || c == 'w' || c == 's' ||
+                      c == 'd';
+            if (!ok) c = '+';
+        }
+        cmd[h] = (uint8_t)c;
+    }
+    int r = sf_rand(e, t) & 1;
+    uint64_t m = live;
+    while (m) {
+        int h = r ? sf_ffs64(m) : sf_fls64(m);
+        m &= ~(1ull << h);
+        sf_obey(d, k, t, env, e, h, cmd[h]);
+        if (e.status != SF_RUNNING) return;
+    }
+}
+
+/* ------------------------------------------------------------------ reset */
+
+/* one arena's overlay is 18,016 bytes, a multiple of 16 and 16-byte aligned */
+SF_FN void sf_clear_grid(uint16_t *g)
+{
+#ifdef __CUDA_ARCH__
+    uint4 *p = reinterpret_cast<uint4 *>(g);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < SF_GRID_STRIDE / 8; ++i) p[i] = zero;
+#else
+    for (int i = 0; i < SF_GRID_STRIDE; ++i) g[i] = 0;
+#endif
+}
+
+/* setup() + load_data() + _srand, gameplay.hpp:1231-1277, 1741-1747, 1861-1920; the harness
+ * then does "++frame" (play(), :1441) */
+SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int64_t tb,
+                        int64_t serial)
+{
+    sf_clear_grid(d.grid + (size_t)env * SF_GRID_STRIDE);
+    int64_t ge = k.env_id_base + env;
+    e.level = k.level_min + (int)(ge % k.level_span);
+    e.frame = 1;
+    e.steps = 0;
+    e.kills = e.tkills = e.loot = e.chest = 0;
+    e.ntemp = 0;
+    e.status = SF_RUNNING;
+    e.quit = 0;
+    e.mz[0] = e.mz[1] = e.mb[0] = e.mb[1] = 0;
+    e.mp[0] = (1ull << k.n_static_exits) - 1ull;
+    e.mp[1] = 0;
+    if (k.mode == SF_MODE_SQUAD) {
+        int c0 = sf_cell_of(0, 3, 1);
+        sf_init_human(d, env, k.player, 0, c0, false, 1, true);
+        SF_G(c0) = (uint16_t)(C_S0 | 0u);
+        for (int i = 1; i < 10; ++i) {
+            int c = i < 5 ? sf_cell_of(0, 1, i + 1) : sf_cell_of(2, 1, i + 1);
+            sf_init_human(d, env, k.npc, i, c, false, i < 5 ? 1 : 2, k.squad_agents != 0);
+            SF_G(c) = (uint16_t)(C_S0 | (uint32_t)i);
+        }
+        e.mh = 0x3FFull;
+        e.hw_h = 10;
+    } else {
+        int c0 = sf_cell_of(0, 1, 1);
+        sf_init_human(d, env, k.player, 0, c0, false, 1, true);
+        SF_G(c0) = (uint16_t)(C_S0 | 0u);
+        e.mh = 1ull;
+        e.hw_h = 1;
+    }
+    sf_srand(e, t, tb, serial);
+}
+
+/* ------------------------------------------------------------------ the step */
+
+/* check_end(), gameplay.hpp:1102-1229, as restated by the harness (eval_end): evaluated at the
+ * end of the step, wall clock replaced by the frame clock (level * 300 s = level * 7500 frames) */
+SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
+{
+    if (e.status != SF_RUNNING) return;
+    if (SF_AT(d.h_hp, 0) <= 0) {
+        e.status = SF_DEAD;
+        return;
+    }
+    if (k.mode == SF_MODE_TIMER) {
+        if ((int64_t)e.frame >= (int64_t)e.level * 7500) e.status = (e.kills < e.level * 5) ? SF_TIMEOUT : SF_WIN;
+    } else if (k.mode == SF_MODE_SOLO) {
+        if (e.level * 5 <= e.kills) e.status = SF_WIN;
+    } else if (e.level * 10 <= e.tkills) {
+        /* rivals_are_dead, gameplay.hpp:497-505 */
+        uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
+        bool alive = false;
+        for (uint64_t m = e.mh; m; m &= m - 1) {
+            uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
+            if (tm && tm != me) alive = true;
+        }
+        if (!alive) e.status = SF_WIN;
+    }
+    if (e.status == SF_RUNNING && k.max_steps > 0 && (int)e.steps >= k.max_steps) e.status = SF_TRUNCATED;
+}
+
+/* first half of the loop body: spawns and half-tick A, gameplay.hpp:1444-1461 */
+SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    if (e.frame % 30 <= 1) sf_spawn_chest(d, k, t, env, e);   /* pc, gameplay.hpp:459 */
+    if (e.status != SF_RUNNING) return;
+    if (e.frame % 40 <= 1) sf_spawn_zombie(d, k, t, env, e);  /* pz */
+    if (e.status != SF_RUNNING) return;
+    if (e.frame % 50 <= 1) sf_spawn_human(d, k, t, env, e);   /* ph */
+    if (e.status != SF_RUNNING) return;
+    sf_zombie_action(d, k, t, env, e);
+    if (e.status != SF_RUNNING) return;
+    sf_portal_damage(d, k, env, e);
+    if (e.status != SF_RUNNING) return;
+    sf_update_tmp(d, k, env, e);
+    sf_hits(d, env, e);
+    e.frame += 1;
+    sf_update_bull(d, t, env, e);
+}
+
+/* second half: human_action and half-tick B, gameplay.hpp:1462-1471, then the victory test */
+SF_FN void sf_step_b(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, const uint8_t *actions)
+{
+    sf_human_action(d, k, t, env, e, actions);
+    if (e.status != SF_RUNNING) return;
+    sf_update_tmp(d, k, env, e);
+    sf_hits(d, env, e);
+    e.frame += 1;
+    sf_update_bull(d, t, env, e);
+    if (e.status != SF_RUNNING) return;
+    e.steps += 1;
+    sf_eval_end(d, k, env, e);
+}
+
+/* ------------------------------------------------------------------ header load / store */
+
+SF_FN void sf_load_env(const SfDev &d, int env, SfEnv &e)
+{
+    e.frame = d.frame[env];
+    e.kills = d.kills[env], e.tkills = d.tkills[env], e.loot = d.loot[env], e.chest = d.chest[env];
+    uint32_t misc = d.misc[env];
+    e.level = (int)(misc & 0xFFu), e.status = (int)((misc >> 8) & 0xFFu), e.hw_h = (int)((misc >> 16) & 0xFFu);
+    e.steps = d.steps[env], e.episode = d.episode[env], e.ntemp = d.ntemp[env];
+    e.mh = d.mh[env];
+    e.mz[0] = SF_AT(d.mz, 0), e.mz[1] = SF_AT(d.mz, 1);
+    e.mb[0] = SF_AT(d.mb, 0), e.mb[1] = SF_AT(d.mb, 1);
+    e.mp[0] = SF_AT(d.mp, 0), e.mp[1] = SF_AT(d.mp, 1);
+    e.quit = 0;
+SF_UNROLL
+    for (int i = 0; i < 18; ++i) {
+        e.L[i] = SF_AT(d.rng_log, i);
+        e.cst[i] = SF_AT(d.rng_cst, i);
+    }
+    e.jomle = d.jomle[env];
+    e.draws = 0;
+}
+
+SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e, bool store_cst)
+{
+    d.frame[env] = e.frame;
+    d.kills[env] = e.kills, d.tkills[env] = e.tkills, d.loot[env] = e.loot, d.chest[env] = e.chest;
+    d.misc[env] = (uint32_t)e.level | ((uint32_t)e.status << 8) | ((uint32_t)e.hw_h << 16);
+    d.steps[env] = e.steps, d.episode[env] = e.episode, d.ntemp[env] = e.ntemp;
+    d.mh[env] = e.mh;
+    SF_AT(d.mz, 0) = e.mz[0], SF_AT(d.mz, 1) = e.mz[1];
+    SF_AT(d.mb, 0) = e.mb[0], SF_AT(d.mb, 1) = e.mb[1];
+    SF_AT(d.mp, 0) = e.mp[0], SF_AT(d.mp, 1) = e.mp[1];
+SF_UNROLL
+    for (int i = 0; i < 18; ++i) {
+        SF_AT(d.rng_log, i) = (uint16_t)e.L[i];
+        if (store_cst) SF_AT(d.rng_cst, i) = e.cst[i];
+    }
+    d.jomle[env] = e.jomle;
+}
+
+/* algorithmic bytes of one step from the live populations:
+ * 2 * (140 + 64 n_h + 12 n_z + 28 n_b + 4 n_c + 8 n_t + 4 n_p) + A_act + 32 */
+SF_FN uint32_t sf_algo_bytes(const SfConst &k, const SfEnv &e)
+{
+    uint32_t nh = (uint32_t)sf_popc64(e.mh), nz = (uint32_t)m2_count(e.mz), nb = (uint32_t)m2_count(e.mb);
+    uint32_t np = (uint32_t)m2_count(e.mp) - (uint32_t)k.n_static_exits;
+    return 2u * (140u + 64u * nh + 12u * nz + 28u * nb + 4u * (uint32_t)e.chest + 8u * e.ntemp + 4u * np) +
+           (uint32_t)k.n_agents + 32u;
+}
+
+
+/* ------------------------------------------------------------------ kernel bodies */
+
+enum { SF_HALF_BOTH = 0, SF_HALF_A = 1, SF_HALF_B = 2 };
+
+/* per-lane contribution to the handle's running statistics (SF_STAT_*) */
+struct SfStatDelta {
+    uint32_t steps, episodes, wins, deaths, timeouts, truncated, overflows, ub_guards, draws, algo_bytes;
+    int32_t kills, tkills, loot;
+};
+
+/* reset one arena for episode `episode` with explicit seeds */
+SF_FN void sf_reset_body(const SfDev &d, const SfConst &k, const SfTabs &t, int env, int64_t tb, int64_t serial,
+                         uint32_t episode)
+{
+    SfEnv e;
+    e.episode = episode;
+    e.draws = 0;
+    sf_reset_env(d, k, t, env, e, tb, serial);
+    sf_store_env(d, env, e, true);
+    sf_step_out o;
+    o.status = SF_RUNNING, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0;
+    o.episode_steps = 0;
+    d.out[env] = o;
+}
+
+/* one env-step (or one half of it) for arena `env`; `actions` is the arena's row of the
+ * action buffer (NULL for SF_HALF_A) */
+SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int env, const uint8_t *actions, int half,
+                        SfStatDelta &sd)
+{
+    SfEnv e;
+    sf_load_env(d, env, e);
+    sf_step_out o;
+    if (half == SF_HALF_B) o = d.out[env];
+    else o.status = 0, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0, o.episode_steps = 0;
+    if (e.status != SF_RUNNING) { /* terminal and not auto-reset: the arena waits for sf_reset */
+        o.status = e.status;
+        o.episode_steps = (int32_t)e.steps;
+        d.out[env] = o;
+        return;
+    }
+    int32_t kills0 = e.kills, tkills0 = e.tkills, loot0 = e.loot;
+    int32_t hp0 = SF_AT(d.h_hp, 0), dmg0 = SF_AT(d.h_dmg, 0), eff0 = SF_AT(d.h_eff, 0);
+    if (half != SF_HALF_B) {
+        sd.algo_bytes += sf_algo_bytes(k, e);
+        sf_step_a(d, k, t, env, e);
+    }
+    if (half != SF_HALF_A && e.status == SF_RUNNING) sf_step_b(d, k, t, env, e, actions);
+    o.d_kills += e.kills - kills0, o.d_teams_kills += e.tkills - tkills0, o.d_loot += e.loot - loot0;
+    o.d_hp += SF_AT(d.h_hp, 0) - hp0, o.d_damage += SF_AT(d.h_dmg, 0) - dmg0, o.d_effect += SF_AT(d.h_eff, 0) - eff0;
+    o.status = e.status;
+    o.episode_steps = (int32_t)e.steps;
+    d.out[env] = o;
+    sd.kills += e.kills - kills0, sd.tkills += e.tkills - tkills0, sd.loot += e.loot - loot0;
+    sd.draws += e.draws;
+    if (half != SF_HALF_A && (e.status == SF_RUNNING || e.status == SF_WIN || e.status == SF_DEAD ||
+                              e.status == SF_TIMEOUT || e.status == SF_TRUNCATED))
+        sd.steps += 1; /* a step that ran to its end (overflow / guard abort it midway) */
+    if (e.status != SF_RUNNING) {
+        sd.episodes += 1;
+        sd.wins += e.status == SF_WIN, sd.deaths += e.status == SF_DEAD, sd.timeouts += e.status == SF_TIMEOUT;
+        sd.truncated += e.status == SF_TRUNCATED, sd.overflows += e.status == SF_OVERFLOW;
+        sd.ub_guards += e.status == SF_UB_GUARD;
+        if (k.auto_reset) { /* new behaviour: next episode of the synthetic seed chain */
+            int64_t ge = k.env_id_base + env;
+            e.episode += 1;
+            e.draws = 0;
+            sf_reset_env(d, k, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode));
+            sf_store_env(d, env, e, true);
+            return;
+        }
+    }
+    sf_store_env(d, env, e, false);
+}
+
+#endif /* SF_CORE_CUH */

@@ -1,0 +1,148 @@
+/*
+ * sf_state.h -- device-resident state of the batched simulator: structure-of-arrays in HBM.
+ *
+ * One arena ("env") of the reference is the global state of one process
+ * (gameplay.hpp:37-55 bull/zomb/hum/portal/mb/active/mz/mh and `gameplay g`, :437-1739).
+ * Here E arenas live side by side.  Every per-entity field is an array indexed
+ * [slot][env] (env minor), so the 32 lanes of a warp -- one lane per arena, all walking the
+ * same slot -- touch 32 consecutive elements.  The only per-arena contiguous block is the
+ * dynamic overlay of the map grid (`grid`, one uint16 per cell), which is addressed by
+ * position, not by slot.
+ *
+ * What is NOT stored per arena: the static map, the item tables and the character
+ * templates (shared constants, SfConst), chest lists (a chest is a cell kind), per-cell
+ * pointers (see below).
+ *
+ * Cell overlay word (uint16), the dynamic part of `struct node` (gameplay.hpp:237-243):
+ *   bits 0-7   slot of the human / zombie standing here (valid under S0 / S1; a cell never
+ *              holds both: humans enter '?^v.X*' cells only, zombies '.' only, :750, :682)
+ *   bit  8     s[0] human     bit 9  s[1] zombie     bit 10  s[2] bullet flag
+ *   bits 11-13 kind: 0 none, 1-4 chest of type kind-1 (s[4] + cons), 5 player-built block
+ *              (s[3]+s[10]), 6 player-built entrance (s[5]+s[10]), 7 player-built exit
+ *              (s[7]+s[10]).  Chests and built objects both need a '.' cell, so they never
+ *              coincide (:536, :706).
+ * The reference's last-writer bullet pointer (node::bullet, trusted only under s[2]) is the
+ * BF_OWNS bit of exactly one live bullet standing in that cell ("last writer").
+ */
+#ifndef SF_STATE_H
+#define SF_STATE_H
+
+#include <stdint.h>
+
+#include "strikeforce_b200.h"
+
+#define SF_GRID_STRIDE 9008 /* SF_CELLS rounded up to a multiple of 16 cells (32 B sectors) */
+
+/* cell overlay bits */
+#define C_OCC 0x00FFu
+#define C_S0 0x0100u
+#define C_S1 0x0200u
+#define C_S2 0x0400u
+#define C_KIND_SHIFT 11
+#define C_KIND (7u << C_KIND_SHIFT)
+enum { K_NONE = 0, K_CHEST0 = 1, K_BLOCK = 5, K_ENTRANCE = 6, K_EXIT = 7 };
+
+/* static map byte */
+#define M_WALL 0x01u
+#define M_UP 0x02u   /* '^' */
+#define M_DOWN 0x04u /* 'v' */
+#define M_EXIT 0x08u /* 'O' */
+#define M_TARGET_SHIFT 4 /* bits 4-7: exit index of a static '^' / 'v' */
+#define SF_MAX_STATIC_EXITS 16
+
+/* what node::showit() prints (gameplay.hpp:321-341) */
+enum { SH_WALL, SH_HUMAN, SH_ZOMBIE, SH_UP, SH_DOWN, SH_BULLET, SH_CHEST, SH_EXIT, SH_DOT };
+
+/* human word h_sel: team | rnpc | agent | vec+1 | ind+1 */
+#define HS_TEAM 0x0003u
+#define HS_RNPC 0x0004u
+#define HS_AGENT 0x0008u
+#define HS_VEC_SHIFT 4 /* 2 bits, stores vec + 1 */
+#define HS_IND_SHIFT 6 /* 4 bits, stores ind + 1 */
+/* position words: cell id in bits 0-13, (way - 1) or `super` in bits 14-15 */
+#define POS_CELL 0x3FFFu
+#define POS_HI_SHIFT 14
+/* bullet word b_meta: range | travelled << 8 | (owner + 1) << 16 | BF_OWNS */
+#define BF_OWNS 0x01000000u
+
+/* hard limits of this layout (sf_create validates the configured caps against them) */
+#define SF_LIM_HUMANS 64
+#define SF_LIM_ZOMBIES 128
+#define SF_LIM_BULLETS 128
+#define SF_LIM_PORTALS 128
+#define SF_LIM_BUILT 4096
+#define SF_MAX_LEVEL 64
+
+typedef struct SfWpn { int32_t stamina, damage, effect, range; } SfWpn;
+
+/* a character as the tick sees it: Human::build (Character.hpp:650-709) already applied */
+typedef struct SfTemplate {
+    int32_t hp, mindamage, stamina;     /* Hp = def_Hp etc. as read from the sheet */
+    int32_t blocks, portals;            /* back_tmp(), Character.hpp:157-162 */
+    uint32_t cons_packed, thr_packed;   /* 4 x uint8 counts */
+    SfWpn thr[4];                       /* upgraded lvl-1 times, Character.hpp:676-680 */
+    SfWpn wpn[8];                       /* upgraded lvl times, :683-686 */
+    int32_t shot_base[8];               /* compute_damage(wpn.damage, wpn.range), :404 */
+    uint32_t w_owned;                   /* bit i: weapon level > 0 */
+    int32_t mindamage_def;              /* after the sheet's own level-ups */
+} SfTemplate;
+
+/* constants shared by every arena of a handle (kernel parameter) */
+typedef struct SfConst {
+    int32_t mode, squad_agents, auto_reset, max_steps, level_min, level_span, n_agents;
+    int32_t cap_h, cap_z, cap_b, cap_chest, cap_t, cap_p;
+    int64_t env_id_base;
+    int32_t n_static_exits;
+    uint16_t static_exit_cell[SF_MAX_STATIC_EXITS];
+    sf_consumable cons[4];
+    SfTemplate player, npc;
+    int32_t player_punch_base;              /* compute_damage(mindamage_def, 1), Character.hpp:393 */
+    int32_t npc_punch_base[SF_MAX_LEVEL + 1]; /* per level: gen_human's level-ups, :883-887 */
+    int32_t npc_mindamage_def[SF_MAX_LEVEL + 1];
+} SfConst;
+
+/* device arrays; E = env stride (n_envs rounded up to 32) */
+typedef struct SfDev {
+    int32_t n_envs, E;
+    /* header */
+    uint32_t *frame;
+    int32_t *kills, *tkills, *loot, *chest;
+    uint32_t *misc;    /* level | status << 8 | hw_h << 16 */
+    uint32_t *steps, *episode, *ntemp;
+    uint64_t *mh, *mz, *mb, *mp; /* live masks: mh[E], mz[2][E], mb[2][E], mp[2][E] */
+    /* random.hpp state in the discrete-log domain */
+    uint16_t *rng_log;  /* [18][E] log_3(random[i]) */
+    uint32_t *rng_cst;  /* [18][E] 2*seed[i] | (2*log_3(us[i])) << 8 */
+    uint32_t *jomle;
+    /* humans [cap_h][E] */
+    uint16_t *h_pw, *h_sel;
+    uint32_t *h_bp;    /* blocks | portals << 8 | (portal_ind + 1) << 16 */
+    int32_t *h_hp, *h_mind, *h_stam, *h_kills, *h_dmg, *h_eff;
+    uint32_t *h_cons, *h_thr;
+    /* zombies [cap_z][E] */
+    uint16_t *z_pos;
+    int32_t *z_hp, *z_mind;
+    /* bullets [cap_b][E] */
+    uint16_t *b_pw;
+    uint32_t *b_meta;
+    int32_t *b_dmg, *b_eff;
+    /* player-built cells [cap_t][E] (gameplay::temp, gameplay.hpp:469) */
+    uint16_t *t_cell;
+    int32_t *t_dmg;
+    uint8_t *t_pidx;
+    /* portal exits [cap_p][E] (portal[], gameplay.hpp:51) */
+    uint16_t *p_cell;
+    /* cell overlay [E][SF_GRID_STRIDE] */
+    uint16_t *grid;
+    /* per-step results and running statistics */
+    sf_step_out *out;
+    unsigned long long *stats; /* [SF_STAT_COUNT] */
+    /* shared tables in global memory */
+    const uint8_t *smap;      /* [SF_CELLS] static map bytes */
+    const uint16_t *exp_tab;  /* [65536] 3^k mod 65537, minus one */
+    const uint16_t *log_tab;  /* [65536] log_3(v) for v = index + 1 */
+    const float *pow_lut;     /* observation transform, see sf_observe */
+    int32_t pow_lut_len;
+} SfDev;
+
+#endif

@@ -166,10 +166,18 @@ int sf_get(sf_handle *h, int32_t field, void *dev_out, void *stream);
    on entry, count on exit.  Synchronises. */
 int sf_export_env(sf_handle *h, int32_t env, int32_t *host_buf, int64_t *n_inout);
 
+/* Replaces Random::_srand + Random::_rand (random.hpp:54-76) for a batch of independent
+   streams: seeds stream i with (tb[i], serial[i]) and writes n_draws outputs per stream into
+   the HOST buffer out_host[draw * n_streams + i].  Known-answer tests use it. */
+int sf_rng_stream(sf_handle *h, const int64_t *tb, const int64_t *serial, int32_t n_streams, int32_t n_draws,
+                  int32_t *out_host);
+
 int32_t sf_agents_per_env(const sf_handle *h);
 int32_t sf_num_envs(const sf_handle *h);
 /* kernels launched by this handle since creation (bench.py's gpu_launches claim) */
 int64_t sf_launch_count(const sf_handle *h);
+/* bytes of HBM held by the handle */
+int64_t sf_device_bytes(const sf_handle *h);
 
 const char *sf_last_error(const sf_handle *h);   /* h == NULL: last sf_create error */
 int32_t sf_abi_version(void);

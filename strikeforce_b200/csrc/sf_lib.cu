@@ -1,0 +1,613 @@
+/*
+ * sf_lib.cu -- CUDA kernels (sm_100a) and the C ABI of include/strikeforce_b200.h.
+ *
+ * Execution model: one thread per arena, one warp per 32 neighbouring arenas,
+ * persistent CTAs (one per SM) whose warps take 32-arena chunks round-robin.  The discrete
+ * exp table of the RNG (128 KB) and the static map (9 KB) are staged in shared memory once
+ * per CTA; per-arena state streams from / to HBM as structure-of-arrays (sf_state.h).  There
+ * is no tensor-core work on this path (no dense contraction) and no CPU fallback: every entry
+ * point fails with SF_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sf_canon_dev.cuh"
+#include "sf_core.cuh"
+#include "sf_host_setup.h"
+#include "sf_obs.cuh"
+
+#define SF_CTA 512
+#define SF_SMEM_EXP 131072
+#define SF_SMEM_MAP 9008
+#define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP)
+#define SF_POW_LUT_LEN (1 << 21)
+#define SF_EXPORT_CAP (1 << 18)
+
+extern __shared__ __align__(16) uint8_t sf_smem[];
+
+/* stage the shared tables: exp table (uint4 copies) and the static map */
+__device__ __forceinline__ void sf_stage_tables(const SfDev &d, SfTabs &t)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(d.exp_tab);
+    uint4 *dst = reinterpret_cast<uint4 *>(sf_smem);
+    for (int i = threadIdx.x; i < SF_SMEM_EXP / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    const uint4 *msrc = reinterpret_cast<const uint4 *>(d.smap); /* padded to SF_SMEM_MAP on the host */
+    uint4 *mdst = reinterpret_cast<uint4 *>(sf_smem + SF_SMEM_EXP);
+    for (int i = threadIdx.x; i < SF_SMEM_MAP / 16; i += blockDim.x) mdst[i] = __ldg(msrc + i);
+    __syncthreads();
+    t.exp_tab = reinterpret_cast<const uint16_t *>(sf_smem);
+    t.smap = sf_smem + SF_SMEM_EXP;
+    t.log_tab = d.log_tab;
+}
+
+__device__ __forceinline__ void sf_flush_stats(const SfDev &d, const SfStatDelta &sd)
+{
+    const unsigned full = 0xffffffffu;
+#define SF_RED(field, slot)                                                        \
+    do {                                                                           \
+        unsigned v = __reduce_add_sync(full, (unsigned)(sd.field));                \
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&d.stats[slot], (unsigned long long)v); \
+    } while (0)
+#define SF_RED_S(field, slot)                                                      \
+    do {                                                                           \
+        int v = (int)__reduce_add_sync(full, (unsigned)(sd.field));                \
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&d.stats[slot], (unsigned long long)(long long)v); \
+    } while (0)
+    SF_RED(steps, SF_STAT_STEPS);
+    SF_RED(episodes, SF_STAT_EPISODES);
+    SF_RED(wins, SF_STAT_WINS);
+    SF_RED(deaths, SF_STAT_DEATHS);
+    SF_RED(timeouts, SF_STAT_TIMEOUTS);
+    SF_RED(truncated, SF_STAT_TRUNCATED);
+    SF_RED(overflows, SF_STAT_OVERFLOWS);
+    SF_RED(ub_guards, SF_STAT_UB_GUARDS);
+    SF_RED(draws, SF_STAT_RNG_DRAWS);
+    SF_RED(algo_bytes, SF_STAT_ALGO_BYTES);
+    SF_RED_S(kills, SF_STAT_KILLS);
+    SF_RED_S(tkills, SF_STAT_TEAMS_KILLS);
+    SF_RED_S(loot, SF_STAT_LOOT);
+#undef SF_RED
+#undef SF_RED_S
+}
+
+/* one env-step (HALF: both halves, A only, B only) for every arena of the handle */
+template <int HALF>
+__global__ void __launch_bounds__(SF_CTA, 1)
+sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *__restrict__ actions)
+{
+    SfTabs t;
+    sf_stage_tables(d, t);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = d.E >> 5;
+    SfStatDelta sd;
+    memset(&sd, 0, sizeof sd);
+    for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
+        int env = chunk * 32 + lane;
+        if (env < d.n_envs)
+            sf_step_body(d, k, t, env, actions ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);
+    }
+    __syncwarp();
+    sf_flush_stats(d, sd);
+}
+
+/* setup() + load_data() + _srand for the listed arenas (all when env_ids == NULL) */
+__global__ void __launch_bounds__(SF_CTA, 1)
+sf_reset_kernel(const SfDev d, const __grid_constant__ SfConst k, const int32_t *__restrict__ env_ids, int n,
+                const int64_t *__restrict__ tb, const int64_t *__restrict__ serial)
+{
+    SfTabs t;
+    sf_stage_tables(d, t);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int env = env_ids ? env_ids[i] : i;
+        int64_t ge = k.env_id_base + env;
+        int64_t tbv = tb ? tb[i] : sf_synth_tb(ge);
+        int64_t sv = serial ? serial[i] : sf_synth_serial(ge, 0);
+        sf_reset_body(d, k, t, env, tbv, sv, 0);
+    }
+}
+
+/* the synthetic action stream of sf_synth.h for global step t */
+__global__ void sf_synth_actions_kernel(uint8_t *actions, int n_envs, int n_agents, int64_t env_id_base, uint64_t step,
+                                        const uint8_t *table, int table_len)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_envs * n_agents) return;
+    int env = i / n_agents, a = i % n_agents;
+    uint64_t z = sf_synth_draw_at(env_id_base + env, a, step);
+    actions[i] = table[z % (uint64_t)table_len];
+}
+
+__device__ __forceinline__ void sf_global_tabs(const SfDev &d, SfTabs &t)
+{
+    t.exp_tab = d.exp_tab, t.log_tab = d.log_tab, t.smap = d.smap;
+}
+
+__global__ void sf_hash_kernel(const SfDev d, const __grid_constant__ SfConst k, uint64_t *out)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    SfTabs t;
+    sf_global_tabs(d, t);
+    SfHashSink sink{0};
+    sf_canon_emit(d, k, t, env, sink);
+    out[env] = sink.sum;
+}
+
+__global__ void sf_export_kernel(const SfDev d, const __grid_constant__ SfConst k, int env, int32_t *buf, long cap,
+                                 long long *n_out)
+{
+    SfTabs t;
+    sf_global_tabs(d, t);
+    SfBufSink sink{buf, cap, 0, false};
+    sf_canon_emit(d, k, t, env, sink);
+    *n_out = sink.overflow ? -1 : sink.n;
+}
+
+__global__ void sf_counters_kernel(const SfDev d, int32_t *out)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    uint32_t misc = d.misc[env];
+    int32_t *o = out + (size_t)env * 8;
+    o[0] = (int32_t)d.frame[env], o[1] = d.kills[env], o[2] = d.tkills[env], o[3] = d.loot[env];
+    o[4] = d.chest[env], o[5] = (int32_t)d.steps[env], o[6] = (int32_t)((misc >> 8) & 0xFFu), o[7] = SF_AT(d.h_hp, 0);
+}
+
+__global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfConst k, int32_t *out)
+{
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    int32_t *o = out + (size_t)env * 6;
+    o[0] = __popcll(d.mh[env]);
+    o[1] = __popcll(SF_AT(d.mz, 0)) + __popcll(SF_AT(d.mz, 1));
+    o[2] = __popcll(SF_AT(d.mb, 0)) + __popcll(SF_AT(d.mb, 1));
+    o[3] = d.chest[env];
+    o[4] = (int32_t)d.ntemp[env];
+    o[5] = __popcll(SF_AT(d.mp, 0)) + __popcll(SF_AT(d.mp, 1));
+}
+
+/* gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158): one CTA per
+ * (arena, selected human).  Stores are channel-major, 4 B per thread, consecutive threads on
+ * consecutive window cells, so every warp store is a run of 128 contiguous bytes. */
+#define SF_OBS_CTA 256
+__global__ void __launch_bounds__(SF_OBS_CTA)
+sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
+                  int nsel)
+{
+    __shared__ int16_t bmap[SF_OBS_CELLS], tmap[SF_OBS_CELLS];
+    const int env = blockIdx.x / nsel;
+    int a = blockIdx.x % nsel;
+    uint32_t m = agent_mask;
+    for (int i = 0; i < a; ++i) m &= m - 1;
+    const int slot = __ffs(m) - 1;
+    float *out = obs + (size_t)blockIdx.x * SF_OBS_LEN;
+    SfTabs t;
+    sf_global_tabs(d, t);
+    SfEnv e;
+    sf_load_env(d, env, e);
+    if (slot >= e.hw_h) { /* a human slot this episode never used: no observer */
+        for (int i = threadIdx.x; i < SF_OBS_LEN; i += SF_OBS_CTA) out[i] = 0.f;
+        return;
+    }
+    const int vcell = (int)(SF_AT(d.h_pw, slot) & POS_CELL);
+    const uint32_t team = SF_AT(d.h_sel, slot) & HS_TEAM;
+    const int fbase = (vcell / (SF_ROWS * SF_COLS)) * (SF_ROWS * SF_COLS);
+    const int r0 = sf_row_of(vcell) - SF_OBS_R, c0 = sf_col_of(vcell) - SF_OBS_R;
+    for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
+    __syncthreads();
+    for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
+        if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
+            int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL) - fbase;
+            if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
+                int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
+                if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN) bmap[wi * SF_OBS_WIN + wj] = (int16_t)b;
+            }
+        }
+    for (int q = threadIdx.x; q < (int)e.ntemp; q += SF_OBS_CTA) {
+        int cell = (int)SF_AT(d.t_cell, q) - fbase;
+        if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
+            int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
+            if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN) tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
+        }
+    }
+    __syncthreads();
+    uint32_t fb = 0;
+    for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
+        int32_t f[32];
+        int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+        sf_describe_milli(d, k, t, env, e, cell, team, bmap[w], tmap[w], f);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[c], &fb);
+    }
+    if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
+}
+
+/* Random::_srand + n _rand() draws for a batch of independent streams (random.hpp:54-76) */
+__global__ void __launch_bounds__(SF_CTA, 1)
+sf_rng_kernel(const SfDev d, const int64_t *tb, const int64_t *serial, int n_streams, int n_draws, int32_t *out)
+{
+    SfTabs t;
+    sf_stage_tables(d, t);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_streams; i += gridDim.x * blockDim.x) {
+        SfEnv e;
+        e.draws = 0;
+        sf_srand(e, t, tb[i], serial[i]);
+        for (int j = 0; j < n_draws; ++j) out[(size_t)j * n_streams + i] = sf_rand(e, t);
+    }
+}
+
+/* ====================================================================== host side */
+
+struct sf_handle {
+    SfDev d;
+    SfConst k;
+    sfhost::Tables tabs;
+    void *arena = nullptr;       /* one device allocation holding every array */
+    size_t arena_bytes = 0;
+    uint8_t *d_actions = nullptr; /* [n_envs][n_agents] staging for sf_step_host / synthetic streams */
+    uint8_t *d_table = nullptr;   /* action alphabet of sf_synth_actions */
+    int32_t *d_export = nullptr;
+    long long *d_export_n = nullptr;
+    int32_t *d_ids = nullptr;
+    int64_t *d_tb = nullptr, *d_serial = nullptr;
+    int device = 0, n_sm = 0;
+    long long launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int sf_fail(sf_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+
+#define SF_CUDA(h, call)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return sf_fail(h, e_ == cudaErrorMemoryAllocation ? SF_ERR_NOMEM : SF_ERR_CUDA,      \
+                           std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+static int sf_require_device(sf_handle *h)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return sf_fail(h, SF_ERR_NO_DEVICE, "no usable CUDA device: strikeforce_b200 has no CPU path");
+    }
+    return SF_OK;
+}
+
+namespace {
+struct Carver {
+    size_t off = 0;
+    uint8_t *base = nullptr;
+    template <class T> void take(T *&p, size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        if (base) p = reinterpret_cast<T *>(base + off);
+        off += n * sizeof(T);
+    }
+};
+
+void carve(Carver &c, sf_handle &h)
+{
+    SfDev &d = h.d;
+    const SfConst &k = h.k;
+    size_t E = (size_t)d.E;
+    c.take(d.frame, E), c.take(d.kills, E), c.take(d.tkills, E), c.take(d.loot, E), c.take(d.chest, E);
+    c.take(d.misc, E), c.take(d.steps, E), c.take(d.episode, E), c.take(d.ntemp, E);
+    c.take(d.mh, E), c.take(d.mz, 2 * E), c.take(d.mb, 2 * E), c.take(d.mp, 2 * E);
+    c.take(d.rng_log, 18 * E), c.take(d.rng_cst, 18 * E), c.take(d.jomle, E);
+    size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)k.cap_t * E;
+    c.take(d.h_pw, H), c.take(d.h_sel, H), c.take(d.h_bp, H), c.take(d.h_hp, H), c.take(d.h_mind, H);
+    c.take(d.h_stam, H), c.take(d.h_kills, H), c.take(d.h_dmg, H), c.take(d.h_eff, H), c.take(d.h_cons, H);
+    c.take(d.h_thr, H);
+    c.take(d.z_pos, Z), c.take(d.z_hp, Z), c.take(d.z_mind, Z);
+    c.take(d.b_pw, B), c.take(d.b_meta, B), c.take(d.b_dmg, B), c.take(d.b_eff, B);
+    c.take(d.t_cell, T), c.take(d.t_dmg, T), c.take(d.t_pidx, T);
+    c.take(d.p_cell, (size_t)k.cap_p * E);
+    c.take(d.grid, E * SF_GRID_STRIDE);
+    c.take(d.out, E);
+    c.take(d.stats, (size_t)SF_STAT_COUNT);
+    uint8_t *smap;
+    uint16_t *exp_tab, *log_tab;
+    float *lut;
+    c.take(smap, (size_t)SF_SMEM_MAP), c.take(exp_tab, (size_t)65536), c.take(log_tab, (size_t)65536);
+    c.take(lut, (size_t)SF_POW_LUT_LEN);
+    d.smap = smap, d.exp_tab = exp_tab, d.log_tab = log_tab, d.pow_lut = lut, d.pow_lut_len = SF_POW_LUT_LEN;
+    c.take(h.d_actions, E * (size_t)k.n_agents);
+    c.take(h.d_table, (size_t)256);
+    c.take(h.d_export, (size_t)SF_EXPORT_CAP);
+    c.take(h.d_export_n, (size_t)1);
+    c.take(h.d_ids, E), c.take(h.d_tb, E), c.take(h.d_serial, E);
+}
+} // namespace
+
+static int sf_launch_reset(sf_handle *h, const int32_t *d_ids, int n, const int64_t *d_tb, const int64_t *d_serial,
+                           cudaStream_t s)
+{
+    int grid = (n + SF_CTA - 1) / SF_CTA;
+    if (grid > h->n_sm) grid = h->n_sm;
+    sf_reset_kernel<<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_ids, n, d_tb, d_serial);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    return SF_OK;
+}
+
+extern "C" {
+
+int32_t sf_abi_version(void) { return SF_ABI_VERSION; }
+
+const char *sf_last_error(const sf_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int sf_create(const sf_config *cfg, sf_handle **out)
+{
+    if (!cfg || !out) return sf_fail(nullptr, SF_ERR_ARG, "sf_create: null argument");
+    *out = nullptr;
+    int rc = sf_require_device(nullptr);
+    if (rc) return rc;
+    sf_handle *h = new (std::nothrow) sf_handle();
+    if (!h) return sf_fail(nullptr, SF_ERR_NOMEM, "host allocation failed");
+    std::string err = sfhost::build_const(*cfg, h->k, h->tabs);
+    if (!err.empty()) {
+        delete h;
+        return sf_fail(nullptr, SF_ERR_ARG, "sf_create: " + err);
+    }
+    memset(&h->d, 0, sizeof h->d);
+    h->d.n_envs = cfg->n_envs;
+    h->d.E = (cfg->n_envs + 31) / 32 * 32;
+    cudaError_t ce = cudaGetDevice(&h->device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    int smem_optin = 0;
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (ce != cudaSuccess) {
+        std::string m = std::string("device query: ") + cudaGetErrorString(ce);
+        delete h;
+        return sf_fail(nullptr, SF_ERR_CUDA, m);
+    }
+    if (smem_optin < SF_SMEM_BYTES) {
+        delete h;
+        return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 140,080 B)");
+    }
+    Carver sizer;
+    carve(sizer, *h);
+    h->arena_bytes = sizer.off + 256;
+    ce = cudaMalloc(&h->arena, h->arena_bytes);
+    if (ce != cudaSuccess) {
+        std::string m = "cudaMalloc of " + std::to_string(h->arena_bytes) + " bytes: " + cudaGetErrorString(ce);
+        delete h;
+        return sf_fail(nullptr, SF_ERR_NOMEM, m);
+    }
+    Carver placer;
+    placer.base = static_cast<uint8_t *>(h->arena);
+    carve(placer, *h);
+#define SF_CREATE_CUDA(call)                                                        \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);    \
+            cudaFree(h->arena);                                                     \
+            delete h;                                                               \
+            return sf_fail(nullptr, SF_ERR_CUDA, m_);                               \
+        }                                                                           \
+    } while (0)
+    SF_CREATE_CUDA(cudaMemset(h->arena, 0, h->arena_bytes));
+    sfhost::build_pow_lut(h->tabs, SF_POW_LUT_LEN);
+    h->tabs.smap.resize(SF_SMEM_MAP, 0);
+    SF_CREATE_CUDA(cudaMemcpy(const_cast<uint8_t *>(h->d.smap), h->tabs.smap.data(), SF_SMEM_MAP, cudaMemcpyHostToDevice));
+    SF_CREATE_CUDA(cudaMemcpy(const_cast<uint16_t *>(h->d.exp_tab), h->tabs.exp_tab.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    SF_CREATE_CUDA(cudaMemcpy(const_cast<uint16_t *>(h->d.log_tab), h->tabs.log_tab.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    SF_CREATE_CUDA(cudaMemcpy(const_cast<float *>(h->d.pow_lut), h->tabs.pow_lut.data(), (size_t)SF_POW_LUT_LEN * 4,
+                              cudaMemcpyHostToDevice));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_step_kernel<SF_HALF_BOTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_step_kernel<SF_HALF_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_step_kernel<SF_HALF_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_rng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    rc = sf_launch_reset(h, nullptr, h->d.n_envs, nullptr, nullptr, 0);
+    if (rc == SF_OK) {
+        cudaError_t e_ = cudaDeviceSynchronize();
+        if (e_ != cudaSuccess) rc = sf_fail(nullptr, SF_ERR_CUDA, std::string("initial reset: ") + cudaGetErrorString(e_));
+    } else
+        g_create_err = h->err;
+    if (rc != SF_OK) {
+        cudaFree(h->arena);
+        delete h;
+        return rc;
+    }
+#undef SF_CREATE_CUDA
+    *out = h;
+    return SF_OK;
+}
+
+int sf_destroy(sf_handle *h)
+{
+    if (!h) return SF_ERR_ARG;
+    cudaDeviceSynchronize();
+    cudaFree(h->arena);
+    delete h;
+    return SF_OK;
+}
+
+int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb, const int64_t *serial, void *stream)
+{
+    if (!h) return SF_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!env_ids) n = h->d.n_envs;
+    if (n <= 0 || n > h->d.n_envs) return sf_fail(h, SF_ERR_ARG, "sf_reset: bad arena count");
+    if ((tb == nullptr) != (serial == nullptr)) return sf_fail(h, SF_ERR_ARG, "sf_reset: tb and serial go together");
+    if (env_ids) {
+        for (int i = 0; i < n; ++i)
+            if (env_ids[i] < 0 || env_ids[i] >= h->d.n_envs) return sf_fail(h, SF_ERR_ARG, "sf_reset: arena id out of range");
+        SF_CUDA(h, cudaMemcpyAsync(h->d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (tb) {
+        for (int i = 0; i < n; ++i)
+            if (tb[i] < 0 || serial[i] < 0) return sf_fail(h, SF_ERR_ARG, "sf_reset: seeds must be non-negative");
+        SF_CUDA(h, cudaMemcpyAsync(h->d_tb, tb, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        SF_CUDA(h, cudaMemcpyAsync(h->d_serial, serial, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    }
+    int rc = sf_launch_reset(h, env_ids ? h->d_ids : nullptr, n, tb ? h->d_tb : nullptr, tb ? h->d_serial : nullptr, s);
+    if (rc) return rc;
+    /* the staging buffers are reused by the next call */
+    SF_CUDA(h, cudaStreamSynchronize(s));
+    return SF_OK;
+}
+
+static int sf_launch_step(sf_handle *h, int half, const uint8_t *d_actions, cudaStream_t s)
+{
+    int nchunks = h->d.E / 32;
+    int grid = (nchunks + SF_CTA / 32 - 1) / (SF_CTA / 32);
+    if (grid > h->n_sm) grid = h->n_sm;
+    if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
+    else if (half == SF_HALF_A) sf_step_kernel<SF_HALF_A><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, nullptr);
+    else sf_step_kernel<SF_HALF_B><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    return SF_OK;
+}
+
+int sf_step(sf_handle *h, const uint8_t *actions, void *stream)
+{
+    if (!h || !actions) return h ? sf_fail(h, SF_ERR_ARG, "sf_step: null actions") : SF_ERR_ARG;
+    return sf_launch_step(h, SF_HALF_BOTH, actions, static_cast<cudaStream_t>(stream));
+}
+
+int sf_step_a(sf_handle *h, void *stream)
+{
+    if (!h) return SF_ERR_ARG;
+    return sf_launch_step(h, SF_HALF_A, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sf_step_b(sf_handle *h, const uint8_t *actions, void *stream)
+{
+    if (!h || !actions) return h ? sf_fail(h, SF_ERR_ARG, "sf_step_b: null actions") : SF_ERR_ARG;
+    return sf_launch_step(h, SF_HALF_B, actions, static_cast<cudaStream_t>(stream));
+}
+
+int sf_step_host(sf_handle *h, const uint8_t *actions_host, sf_step_out *out_host, void *stream)
+{
+    if (!h || !actions_host || !out_host) return h ? sf_fail(h, SF_ERR_ARG, "sf_step_host: null argument") : SF_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    size_t na = (size_t)h->d.n_envs * (size_t)h->k.n_agents;
+    SF_CUDA(h, cudaMemcpyAsync(h->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
+    int rc = sf_launch_step(h, SF_HALF_BOTH, h->d_actions, s);
+    if (rc) return rc;
+    SF_CUDA(h, cudaMemcpyAsync(out_host, h->d.out, (size_t)h->d.n_envs * sizeof(sf_step_out), cudaMemcpyDeviceToHost, s));
+    SF_CUDA(h, cudaStreamSynchronize(s));
+    return SF_OK;
+}
+
+int sf_synth_actions(sf_handle *h, uint8_t *actions, uint64_t t, const char *table, int32_t table_len, void *stream)
+{
+    if (!h || !actions || !table || table_len <= 0 || table_len > 256)
+        return h ? sf_fail(h, SF_ERR_ARG, "sf_synth_actions: bad argument") : SF_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SF_CUDA(h, cudaMemcpyAsync(h->d_table, table, (size_t)table_len, cudaMemcpyHostToDevice, s));
+    int n = h->d.n_envs * h->k.n_agents;
+    sf_synth_actions_kernel<<<(n + 255) / 256, 256, 0, s>>>(actions, h->d.n_envs, h->k.n_agents, h->k.env_id_base, t,
+                                                            h->d_table, table_len);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    return SF_OK;
+}
+
+int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, void *stream)
+{
+    if (!h || !obs) return h ? sf_fail(h, SF_ERR_ARG, "sf_observe: null buffer") : SF_ERR_ARG;
+    if (phase != SF_OBS_P1 && phase != SF_OBS_P2) return sf_fail(h, SF_ERR_ARG, "sf_observe: phase must be SF_OBS_P1 or SF_OBS_P2");
+    int nsel = __builtin_popcount(agent_mask);
+    if (nsel == 0) return sf_fail(h, SF_ERR_ARG, "sf_observe: empty agent mask");
+    sf_observe_kernel<<<h->d.n_envs * nsel, SF_OBS_CTA, 0, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
+                                                                                               nsel);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    return SF_OK;
+}
+
+int sf_get(sf_handle *h, int32_t field, void *dev_out, void *stream)
+{
+    if (!h || !dev_out) return h ? sf_fail(h, SF_ERR_ARG, "sf_get: null buffer") : SF_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int n = h->d.n_envs, grid = (n + 127) / 128;
+    switch (field) {
+    case SF_FIELD_STEP_OUT:
+        SF_CUDA(h, cudaMemcpyAsync(dev_out, h->d.out, (size_t)n * sizeof(sf_step_out), cudaMemcpyDeviceToDevice, s));
+        return SF_OK;
+    case SF_FIELD_STATS:
+        SF_CUDA(h, cudaMemcpyAsync(dev_out, h->d.stats, SF_STAT_COUNT * 8, cudaMemcpyDeviceToDevice, s));
+        return SF_OK;
+    case SF_FIELD_STATE_HASH:
+        sf_hash_kernel<<<grid, 128, 0, s>>>(h->d, h->k, static_cast<uint64_t *>(dev_out));
+        break;
+    case SF_FIELD_COUNTERS:
+        sf_counters_kernel<<<grid, 128, 0, s>>>(h->d, static_cast<int32_t *>(dev_out));
+        break;
+    case SF_FIELD_POPULATION:
+        sf_population_kernel<<<grid, 128, 0, s>>>(h->d, h->k, static_cast<int32_t *>(dev_out));
+        break;
+    default:
+        return sf_fail(h, SF_ERR_ARG, "sf_get: unknown field");
+    }
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    return SF_OK;
+}
+
+int sf_export_env(sf_handle *h, int32_t env, int32_t *host_buf, int64_t *n_inout)
+{
+    if (!h || !host_buf || !n_inout) return h ? sf_fail(h, SF_ERR_ARG, "sf_export_env: null argument") : SF_ERR_ARG;
+    if (env < 0 || env >= h->d.n_envs) return sf_fail(h, SF_ERR_ARG, "sf_export_env: arena id out of range");
+    SF_CUDA(h, cudaDeviceSynchronize());
+    sf_export_kernel<<<1, 1>>>(h->d, h->k, env, h->d_export, (long)SF_EXPORT_CAP, h->d_export_n);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    long long n = 0;
+    SF_CUDA(h, cudaMemcpy(&n, h->d_export_n, sizeof n, cudaMemcpyDeviceToHost));
+    if (n < 0 || n > *n_inout) return sf_fail(h, SF_ERR_ARG, "sf_export_env: buffer too small");
+    SF_CUDA(h, cudaMemcpy(host_buf, h->d_export, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    *n_inout = n;
+    return SF_OK;
+}
+
+int sf_rng_stream(sf_handle *h, const int64_t *tb, const int64_t *serial, int32_t n_streams, int32_t n_draws,
+                  int32_t *out_host)
+{
+    if (!h || !tb || !serial || !out_host || n_streams <= 0 || n_draws <= 0)
+        return h ? sf_fail(h, SF_ERR_ARG, "sf_rng_stream: bad argument") : SF_ERR_ARG;
+    int64_t *d_tb = nullptr, *d_serial = nullptr;
+    int32_t *d_out = nullptr;
+    size_t n_out = (size_t)n_streams * (size_t)n_draws;
+    SF_CUDA(h, cudaMalloc(&d_tb, (size_t)n_streams * 8));
+    SF_CUDA(h, cudaMalloc(&d_serial, (size_t)n_streams * 8));
+    SF_CUDA(h, cudaMalloc(&d_out, n_out * 4));
+    SF_CUDA(h, cudaMemcpy(d_tb, tb, (size_t)n_streams * 8, cudaMemcpyHostToDevice));
+    SF_CUDA(h, cudaMemcpy(d_serial, serial, (size_t)n_streams * 8, cudaMemcpyHostToDevice));
+    int grid = (n_streams + SF_CTA - 1) / SF_CTA;
+    if (grid > h->n_sm) grid = h->n_sm;
+    sf_rng_kernel<<<grid, SF_CTA, SF_SMEM_BYTES>>>(h->d, d_tb, d_serial, n_streams, n_draws, d_out);
+    h->launches += 1;
+    SF_CUDA(h, cudaGetLastError());
+    SF_CUDA(h, cudaMemcpy(out_host, d_out, n_out * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_tb), cudaFree(d_serial), cudaFree(d_out);
+    return SF_OK;
+}
+
+int32_t sf_agents_per_env(const sf_handle *h) { return h ? h->k.n_agents : 0; }
+int32_t sf_num_envs(const sf_handle *h) { return h ? h->d.n_envs : 0; }
+int64_t sf_launch_count(const sf_handle *h) { return h ? h->launches : 0; }
+int64_t sf_device_bytes(const sf_handle *h) { return h ? (int64_t)h->arena_bytes : 0; }
+
+} /* extern "C" */

@@ -1,0 +1,47 @@
+"""Shared helpers of the parity tests: drive the C oracle (oracle/sf_oracle.c) and a device
+or host-check simulator with the same seeds and action streams and compare canonical state."""
+import numpy as np
+
+import sfo
+from strikeforce_b200 import config as sfcfg
+
+SYNTH_TB0 = 1700000000
+
+
+def synth_tb(e):
+    return SYNTH_TB0 + e
+
+
+def synth_serial(e, k=0):
+    return (123456789 + 7919 * e + 104729 * k) & ((1 << 30) - 1)
+
+
+def splitmix_draw(e, agent, t):
+    """include/sf_synth.h sf_synth_draw_at"""
+    m = (1 << 64) - 1
+    s = (42 + e * 1000003 + agent + t * 0x9E3779B97F4A7C15) & m
+    z = (s + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+def synth_actions(env_ids, n_agents, t, table):
+    out = np.empty((len(env_ids), n_agents), dtype=np.uint8)
+    for i, e in enumerate(env_ids):
+        for a in range(n_agents):
+            out[i, a] = table[splitmix_draw(e, a, t) % len(table)]
+    return out
+
+
+def make_oracles(arena_data, n_envs, mode, level, squad_agents=False, player="account1", max_steps=0, caps=None,
+                 env_id_base=0):
+    cfg = sfcfg.make_config(arena_data, mode=mode, level_min=level, squad_agents=squad_agents, max_steps=max_steps,
+                            player=player, caps=caps)
+    arenas = []
+    for e in range(n_envs):
+        a = sfo.Arena(cfg)
+        ge = env_id_base + e
+        a.reset(level, synth_tb(ge), synth_serial(ge, 0))
+        arenas.append(a)
+    return arenas

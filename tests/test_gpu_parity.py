@@ -1,0 +1,139 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the C oracle on the same
+seeded inputs (bit-exact: state hash of the canonical record every step, step outputs,
+observations as fp32 words)."""
+import numpy as np
+import pytest
+
+import common
+from strikeforce_b200 import config as sfcfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback to test")
+    return torch
+
+
+def _run_parity(torch, arena_data, mode, level, n_envs, steps, table, squad_agents=False, player="account1",
+                max_steps=0, caps=None, obs_every=0, obs_mask=1):
+    from strikeforce_b200.sim import BatchedArena
+    sim = BatchedArena(n_envs, mode=mode, level=level, squad_agents=squad_agents, auto_reset=False,
+                       max_steps=max_steps, player=player, caps=caps)
+    oracles = common.make_oracles(arena_data, n_envs, mode, level, squad_agents, player, max_steps, caps)
+    try:
+        h_dev = sim.state_hash().cpu().numpy().view(np.uint64)
+        h_ora = np.array([o.state_hash() for o in oracles], dtype=np.uint64)
+        assert (h_dev == h_ora).all(), "state after reset differs"
+        done = np.zeros(n_envs, dtype=bool)
+        for t in range(steps):
+            act = sim.synth_actions(t, table)
+            act_h = act.cpu().numpy()
+            assert (act_h == common.synth_actions(range(n_envs), sim.n_agents, t, table)).all()
+            sim.step(act)
+            out = sim.step_out().cpu().numpy()
+            for e, o in enumerate(oracles):
+                o.step(bytes(act_h[e]))
+                so = o.step_out()
+                assert out[e, 0] == so["status"], "status differs: env %d step %d: %d vs %d" % (e, t, out[e, 0], so["status"])
+                if so["status"] in (sfcfg.RUNNING, sfcfg.WIN, sfcfg.DEAD, sfcfg.TIMEOUT, sfcfg.TRUNCATED) and not done[e]:
+                    ref = [so[k] for k in ("status", "d_kills", "d_teams_kills", "d_loot", "d_hp", "d_damage",
+                                           "d_effect", "episode_steps")]
+                    assert out[e].tolist() == ref, "step_out differs: env %d step %d" % (e, t)
+                done[e] |= so["status"] != sfcfg.RUNNING
+            h_dev = sim.state_hash().cpu().numpy().view(np.uint64)
+            for e, o in enumerate(oracles):
+                if o.status() in (sfcfg.OVERFLOW, sfcfg.UB_GUARD):
+                    continue  # aborted mid-step: only the status is defined
+                if h_dev[e] != np.uint64(o.state_hash()):
+                    diff = sfo_diff(o, sim, e)
+                    pytest.fail("state differs: env %d step %d\n%s" % (e, t, "\n".join(diff)))
+            if obs_every and t % obs_every == 0:
+                nsel = bin(obs_mask).count("1")
+                obs = sim.observe(agent_mask=obs_mask).cpu().numpy().reshape(n_envs, nsel, -1)
+                slots = [i for i in range(32) if (obs_mask >> i) & 1]
+                for e, o in enumerate(oracles):
+                    for j, slot in enumerate(slots):
+                        try:
+                            ref = o.observe(slot)
+                        except RuntimeError:
+                            continue  # no active agent on that slot: the reference builds nothing
+                        assert (obs[e, j].view(np.uint32) == ref.view(np.uint32)).all(), \
+                            "observation differs: env %d slot %d step %d" % (e, slot, t)
+        return sim.stats()
+    finally:
+        sim.close()
+
+
+def sfo_diff(oracle, sim, env):
+    import sfo
+    return sfo.diff_records(oracle.dump(), sim.export_env(env))
+
+
+def test_rng_known_answers(torch_cuda, arena_data):
+    """random.hpp:54-76 on the device against the reference's known answers and the oracle."""
+    import sfo
+    from strikeforce_b200.sim import BatchedArena
+    sim = BatchedArena(32)
+    try:
+        tb = [1700000000, 0, 1771155561] + [1700000000 + i for i in range(200)]
+        serial = [123456789, 0, 1073741823] + [common.synth_serial(i) for i in range(200)]
+        out = sim.rng_stream(tb, serial, 64)
+        assert out[:16, 0].tolist() == [285, 813, 468, 757, 905, 105, 521, 980, 354, 530, 55, 911, 702, 226, 255, 98]
+        assert out[:8, 1].tolist() == [669, 110, 539, 452, 774, 356, 42, 334]
+        assert out[:8, 2].tolist() == [881, 744, 641, 806, 562, 855, 824, 187]
+        for i in range(len(tb)):
+            r = sfo.Rng(tb[i], serial[i])
+            assert out[:, i].tolist() == [r.rand() for _ in range(64)]
+    finally:
+        sim.close()
+
+
+def test_solo_parity(torch_cuda, arena_data):
+    st = _run_parity(torch_cuda, arena_data, sfcfg.MODE_SOLO, 1, 96, 400, sfcfg.ACTIONS9, obs_every=50)
+    assert st["steps"] == 96 * 400
+
+
+def test_timer_parity_full_alphabet(torch_cuda, arena_data):
+    _run_parity(torch_cuda, arena_data, sfcfg.MODE_TIMER, 2, 64, 600, sfcfg.ACTIONS28, player="synthetic", obs_every=100)
+
+
+def test_squad_parity(torch_cuda, arena_data):
+    _run_parity(torch_cuda, arena_data, sfcfg.MODE_SQUAD, 1, 64, 600, sfcfg.ACTIONS28, obs_every=100)
+
+
+def test_squad_agents_parity(torch_cuda, arena_data):
+    _run_parity(torch_cuda, arena_data, sfcfg.MODE_SQUAD, 3, 48, 500, sfcfg.ACTIONS9, squad_agents=True, obs_every=100,
+                obs_mask=0b1000001001)
+
+
+def test_long_episode_parity(torch_cuda, arena_data):
+    """Mid-episode populations (dozens of zombies, NPC-built blocks and portals)."""
+    _run_parity(torch_cuda, arena_data, sfcfg.MODE_SOLO, 1, 8, 2500, sfcfg.ACTIONS28, obs_every=500)
+
+
+def test_overflow_and_truncation_status(torch_cuda, arena_data):
+    caps = dict(cap_humans=12, cap_zombies=8, cap_bullets=6, cap_built=8, cap_portals=8)
+    _run_parity(torch_cuda, arena_data, sfcfg.MODE_SOLO, 1, 32, 400, sfcfg.ACTIONS28, caps=caps, max_steps=300)
+
+
+def test_step_host_matches_device_step(torch_cuda, arena_data):
+    from strikeforce_b200.sim import BatchedArena
+    a = BatchedArena(64, mode="Solo", auto_reset=True, max_steps=50)
+    b = BatchedArena(64, mode="Solo", auto_reset=True, max_steps=50)
+    try:
+        out_h = np.zeros(64, dtype=sfcfg.STEP_OUT_DTYPE)
+        for t in range(120):  # crosses two auto-resets
+            act = a.synth_actions(t)
+            a.step(act)
+            b.step_host(act.cpu().numpy(), out_h)
+            out_d = a.step_out().cpu().numpy()
+            assert (out_d == out_h.view(np.int32).reshape(64, 8)).all()
+        assert (a.state_hash() == b.state_hash()).all()
+        st = a.stats()
+        assert st["episodes"] == 64 * 2 and st["truncated"] + st["deaths"] + st["wins"] == st["episodes"]
+    finally:
+        a.close(), b.close()

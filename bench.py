@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched StrikeForce tick on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "squad5v5"): Squad 5v5 with NPC spawns under the reference's
+shipped macros (squad mates and opponents idle unless USE_AGENT_IN_SQUAD_NPCS, macros.hpp:14;
+spawned NPC humans and zombies act every step), levels 1-10 round-robin over arenas, the player
+driven by the 28-symbol command alphabet (blocks and portals enabled), 131,072 arenas per GPU (BASELINE.json configs[3]:
+1M arenas over 8 GPUs; weak scaling), episodes truncated at 2,048 steps and re-created in the
+same call, synthetic seeds and action streams of include/sf_synth.h.  Before timing, the arenas
+are spread over episode ages (16 staggered partial resets during the untimed set-up) so that the
+timed steps see mid-episode populations, not empty maps.
+
+One step = one sf_step over every arena of the rank.  `value` times K steps with actions already
+resident in HBM (CUDA events); `e2e` times the same K steps through sf_step_host with HOST
+buffers (pinned actions in, sf_step_out back) inside the timed region.  `roofline` is the step
+kernel: algorithmic bytes (summed on the device from the live populations) over its
+CUDA-event duration against MEASURED_PEAKS.json.  `cpu_baseline` / `--impl reference` time the
+UNMODIFIED reference tick engine (oracle/_ref/libsfref.so, one process per arena because the
+reference keeps its state in globals) on the box's host cores, on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(workload="squad5v5", mode="Squad", squad_agents=False, level_min=1, level_max=10,
+                envs_per_gpu=131072, max_steps=2048, alphabet="28-symbol valid_commands minus '3'",
+                l2="state per GPU (3.5 GB) far exceeds the 126 MB L2; no flush needed")
+METRIC = "env-steps/sec (bit-exact)"
+UNIT = "env-steps/s"
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+
+def _ref_worker(args):
+    """One process = one arena of the unmodified reference (its state is global)."""
+    env, level, n_steps, with_obs = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfref
+    from strikeforce_b200 import config as sfcfg
+    caps = [sfcfg.DEFAULT_CAPS[k] for k in ("cap_humans", "cap_zombies", "cap_bullets", "cap_chests", "cap_built",
+                                            "cap_portals")]
+    sfref.lib()
+    t0 = time.perf_counter()
+    n, _ = sfref.run_stream(env, sfcfg.MODE_SQUAD, level, n_steps, sfcfg.ACTIONS28.decode(), squad_agents=WORKLOAD["squad_agents"],
+                            caps=caps, max_steps=WORKLOAD["max_steps"], with_obs=with_obs)
+    return n, time.perf_counter() - t0
+
+
+def _port_worker(args):
+    env, level, n_steps, with_obs = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfo
+    from strikeforce_b200 import config as sfcfg
+    from strikeforce_b200 import data as sfdata
+    cfg = sfcfg.make_config(sfdata.load_default(), mode=sfcfg.MODE_SQUAD, level_min=level, squad_agents=WORKLOAD["squad_agents"],
+                            max_steps=WORKLOAD["max_steps"])
+    a = sfo.Arena(cfg)
+    t0 = time.perf_counter()
+    n, _ = a.run_stream(env, level, n_steps, sfcfg.ACTIONS28, with_obs=with_obs)
+    return n, time.perf_counter() - t0
+
+
+def cpu_reference(steps_per_arena, passes=1, with_obs=False):
+    """Times the reference's own CPU implementation on all host cores.  Returns a dict for
+    the `cpu_baseline` key.  Each arena plays one full truncated episode cycle per pass, the
+    same age mix the GPU arm sees."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfref
+    cores = os.cpu_count() or 1
+    kind = "reference" if sfref.available() else "port"
+    worker = _ref_worker if kind == "reference" else _port_worker
+    jobs = [(e, 1 + e % 10, steps_per_arena, with_obs) for e in range(cores * passes)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    total = sum(n for n, _ in res)
+    busy = sum(t for _, t in res)
+    span = max(t for _, t in res) * passes  # all cores run side by side; process start-up excluded
+    return dict(value=total / span, unit=UNIT, cores=cores, kind=kind, per_core=total / busy,
+                sample="%d arenas (one process each, %d at a time) x %d steps of squad5v5 incl. auto-reset; "
+                       "%.1f s of stepping, %.1f s wall with process start-up" % (len(jobs), cores, steps_per_arena,
+                                                                                 span, wall))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- our arm
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from strikeforce_b200 import config as sfcfg
+    from strikeforce_b200.sim import BatchedArena
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    E = args.envs
+    K, W = args.steps, args.warmup
+    table = sfcfg.ACTIONS28
+    sim = BatchedArena(E, mode="Squad", level=WORKLOAD["level_min"], level_max=WORKLOAD["level_max"],
+                       squad_agents=WORKLOAD["squad_agents"], auto_reset=True, max_steps=WORKLOAD["max_steps"], env_id_base=rank * E)
+    A = sim.n_agents
+    # ---- untimed set-up: spread the arenas over episode ages
+    t = 0
+    buckets = 16
+    per = max(1, args.prewarm // buckets)
+    ids_all = np.arange(E, dtype=np.int32)
+    for j in range(buckets):
+        for _ in range(per):
+            sim.step(sim.synth_actions(t, table))
+            t += 1
+        if j + 1 < buckets:
+            sim.reset(ids_all[ids_all % buckets == j])
+    for _ in range(W):
+        sim.step(sim.synth_actions(t, table))
+        t += 1
+    torch.cuda.synchronize()
+    pop = sim.population().float().mean(0).tolist()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, actions already in HBM
+    acts = [sim.synth_actions(t + i, table, out=torch.empty((E, A), dtype=torch.uint8, device=sim.device))
+            for i in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st0 = sim.stats_tensor().clone()
+    l0 = sim.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        sim.step(acts[i])
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = sim.launches - l0
+    st1 = sim.stats_tensor().clone()
+    t += K
+    # ---- end-to-end timing: host actions in, step results out, every step
+    acts_h = [a.cpu().pin_memory() for a in
+              [sim.synth_actions(t + i, table, out=torch.empty((E, A), dtype=torch.uint8, device=sim.device))
+               for i in range(K)]]
+    out_h = torch.empty((E, 8), dtype=torch.int32).pin_memory()
+    out_np = out_h.numpy().view(sfcfg.STEP_OUT_DTYPE).reshape(E)
+    for i in range(min(W, K)):
+        sim.step_host(acts_h[i].numpy(), out_np)  # untimed warm-up of the copy path
+    st2 = sim.stats_tensor().clone()
+    barrier()
+    w0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        sim.step_host(acts_h[i].numpy(), out_np)
+    e1.record()
+    barrier()
+    ms_e2e_wall = (time.perf_counter() - w0) * 1e3
+    ms_e2e = max(e0.elapsed_time(e1), ms_e2e_wall)
+    st3 = sim.stats_tensor().clone()
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+    # ---- reduce over ranks: max time, summed statistics (the only collective: NCCL all-reduce)
+    tm = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=sim.device)
+    d_dev, d_e2e = (st1 - st0), (st3 - st2)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d_dev, op=dist.ReduceOp.SUM)
+        dist.all_reduce(d_e2e, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e = tm.cpu().tolist()
+    names = sfcfg.STAT_NAMES
+    d_dev = dict(zip(names, d_dev.cpu().tolist()))
+    d_e2e = dict(zip(names, d_e2e.cpu().tolist()))
+    local_algo = float((st1 - st0)[names.index("algo_bytes")].item())
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        steps_done = d_dev["steps"] + d_dev["overflows"] + d_dev["ub_guards"]
+        value = steps_done / (ms_dev / 1e3)
+        e2e_steps = d_e2e["steps"] + d_e2e["overflows"] + d_e2e["ub_guards"]
+        achieved = local_algo / (ms_dev / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic (seeded maps/seeds and splitmix64 action streams, include/sf_synth.h)",
+            "config": dict(WORKLOAD, envs_per_gpu=E, agents_per_env=A, prewarm_steps=args.prewarm,
+                           mean_population=dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"],
+                                                    [round(x, 2) for x in pop]))),
+            "e2e": {"value": e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": E * A * world,
+                    "d2h_bytes_per_step": E * 32 * world, "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "sf_step_kernel<0>",
+                         "algo_bytes_per_env_step": local_algo / max(1, K * E),
+                         "note": "per GPU (rank 0); algorithmic bytes summed on the device from live populations"},
+            "clocks": sampler.summary(),
+            "episodes": {k: d_dev[k] for k in ("episodes", "wins", "deaths", "timeouts", "truncated", "overflows",
+                                               "ub_guards")},
+            "rng_draws_per_env_step": d_dev["rng_draws"] / max(1, steps_done),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_reference(args.cpu_steps)
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # one "step" of this arm = a bounded sample: every host core plays cpu_steps env-steps
+    vals, last = [], None
+    for i in range(W + K):
+        last = cpu_reference(args.ref_steps)
+        if i >= W:
+            vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic (seeded maps/seeds and splitmix64 action streams, include/sf_synth.h)",
+        "config": dict(WORKLOAD, envs_per_gpu=args.envs, agents_per_env=1),
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=WORKLOAD["envs_per_gpu"], help="arenas per GPU")
+    ap.add_argument("--prewarm", type=int, default=2048, help="untimed set-up steps (age spreading)")
+    ap.add_argument("--cpu-steps", type=int, default=16384, help="env-steps per host core for cpu_baseline")
+    ap.add_argument("--ref-steps", type=int, default=8192, help="env-steps per host core per reference-arm step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,7 +102,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         f[2] = (g & C_S1) ? 1 : 0, f[3] = (g & C_S1) ? (int32_t)(g & C_OCC) : -1;
         f[4] = (g & C_S2) ? 1 : 0, f[5] = bidx;
         f[6] = chest ? 1 : 0, f[7] = chest ? (int32_t)kind - K_CHEST0 : -1;
-        f[8] = built, f[9] = q >= 0 ? SF_AT(d.t_dmg, q) : 0, f[10] = built == 2 ? (int32_t)SF_AT(d.t_pidx, q) : -1;
+        f[8] = built, f[9] = q >= 0 ? SF_T(d.t_dmg, q) : 0, f[10] = built == 2 ? (int32_t)SF_T(d.t_pidx, q) : -1;
         sink.elem(SF_K_CELL, cell, f, SF_NF_CELL);
     }
 }

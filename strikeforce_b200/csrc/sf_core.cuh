@@ -27,6 +27,18 @@
 #define SF_UNROLL
 #endif
 
+/* Warp-lockstep helpers.  The device runs one arena per lane; every loop of the tick has a
+ * warp-uniform trip count (the maximum over the 32 lanes) and ends each iteration with
+ * SF_SYNCWARP(), and no lane leaves a phase early (a failed arena just turns `e.on` off), so
+ * the 32 lanes re-converge after every divergent branch instead of drifting apart. */
+#ifdef __CUDA_ARCH__
+#define SF_SYNCWARP() __syncwarp()
+#define SF_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (int)(x))
+#else
+#define SF_SYNCWARP() ((void)0)
+#define SF_WARP_MAX(x) ((int)(x))
+#endif
+
 #define SF_RNG_ZERO 0x10000u /* log-domain marker of the value 0 (only during the warm-up) */
 
 /* tables every lane reads: shared memory on the device, plain arrays in the host check */
@@ -43,6 +55,7 @@ struct SfEnv {
     int32_t level, status, hw_h;
     uint64_t mh, mz[2], mb[2], mp[2];
     uint64_t quit;       /* humans whose Hp was zeroed by '_' (gameplay.hpp:696-699) */
+    bool on;             /* this lane holds an arena that is still running this step */
     uint32_t L[18];      /* log_3 of random[0..17] (random.hpp:31) */
     uint32_t cst[18];    /* 2*seed[i] | 2*log_3(us[i]) << 8 */
     uint32_t draws;      /* _rand() calls in this kernel (statistics) */
@@ -123,6 +136,8 @@ SF_FN int m2_prev(const uint64_t m[2], int i)
 /* ------------------------------------------------------------------ addressing */
 
 #define SF_AT(arr, slot) (arr)[(size_t)(slot) * (size_t)d.E + (size_t)env]
+/* player-built records are contiguous per arena (they are searched by cell, not walked) */
+#define SF_T(arr, q) (arr)[(size_t)env * (size_t)d.cap_t + (size_t)(q)]
 #define SF_G(cell) d.grid[(size_t)env * SF_GRID_STRIDE + (size_t)(cell)]
 
 SF_FN int sf_cell_of(int f, int r, int c) { return (f * SF_ROWS + r) * SF_COLS + c; }
@@ -214,6 +229,13 @@ SF_FN int sf_punch_base(const SfConst &k, const SfEnv &e, int h)
     return h == 0 ? k.player_punch_base : k.npc_punch_base[e.level];
 }
 
+/* an arena that needs a slot beyond its configured capacity stops (harness: SF_OVERFLOW) */
+SF_FN void sf_fail_env(SfEnv &e, int status)
+{
+    e.status = status;
+    e.on = false;
+}
+
 /* write every field of human slot h: Human::build + gen_human (Character.hpp:650-709, 873-888)
  * or the `hum[ind] = me` copy of load_data (gameplay.hpp:1864, 1909) */
 SF_FN void sf_init_human(const SfDev &d, int env, const SfTemplate &tp, int h, int cell, bool rnpc, int team,
@@ -232,13 +254,13 @@ SF_FN void sf_init_human(const SfDev &d, int env, const SfTemplate &tp, int h, i
     SF_AT(d.h_thr, h) = tp.thr_packed;
 }
 
-/* lowest free bullet slot (b_ind, gameplay.hpp:230-235); a slot at or beyond the configured
- * capacity is the harness's SF_OVERFLOW */
+/* lowest free bullet slot (b_ind, gameplay.hpp:230-235); -1 and the arena fails when it lies
+ * at or beyond the configured capacity */
 SF_FN int sf_alloc_bullet(const SfConst &k, SfEnv &e)
 {
     int b = m2_lowest_free(e.mb);
     if (b >= k.cap_b) {
-        e.status = SF_OVERFLOW;
+        sf_fail_env(e, SF_OVERFLOW);
         return -1;
     }
     m2_set(e.mb, b);
@@ -251,12 +273,11 @@ SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, u
                            int owner, int dmg, int eff)
 {
     if (g & C_S2) {
-        for (int o = m2_next(e.mb, 0); o >= 0; o = m2_next(e.mb, o + 1)) {
-            if (o == b) continue;
-            uint32_t m = SF_AT(d.b_meta, o);
-            if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) {
-                SF_AT(d.b_meta, o) = m & ~BF_OWNS;
-                break;
+        int hi = m2_highest(e.mb);
+        for (int o = 0; o <= hi; ++o) {
+            if (o != b && m2_test(e.mb, o)) {
+                uint32_t m = SF_AT(d.b_meta, o);
+                if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) SF_AT(d.b_meta, o) = m & ~BF_OWNS;
             }
         }
     }
@@ -267,32 +288,49 @@ SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, u
     SF_G(cell) = (uint16_t)(g | C_S2);
 }
 
-/* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469) */
+/* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469), -1 if none */
 SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
 {
+    int found = -1;
+    const uint16_t *tc = &SF_T(d.t_cell, 0);
+#ifdef __CUDA_ARCH__
+    /* the per-arena record block is 16-byte aligned (cap_t is a multiple of 8) */
+    const uint4 *tv = reinterpret_cast<const uint4 *>(tc);
+    const uint32_t want = (uint32_t)cell;
+    for (uint32_t q0 = 0; q0 < e.ntemp; q0 += 8) {
+        uint4 v = tv[q0 >> 3];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if ((w[j] & 0xFFFFu) == want && q0 + 2 * j < e.ntemp) found = (int)(q0 + 2 * j);
+            if ((w[j] >> 16) == want && q0 + 2 * j + 1 < e.ntemp) found = (int)(q0 + 2 * j + 1);
+        }
+    }
+#else
     for (uint32_t q = 0; q < e.ntemp; ++q)
-        if (SF_AT(d.t_cell, q) == cell) return (int)q;
-    return -1;
+        if (tc[q] == cell) found = (int)q;
+#endif
+    return found;
 }
 SF_FN void sf_remove_built(const SfDev &d, int env, SfEnv &e, int q)
 {
     uint32_t last = e.ntemp - 1;
     if ((uint32_t)q != last) {
-        SF_AT(d.t_cell, q) = SF_AT(d.t_cell, last);
-        SF_AT(d.t_dmg, q) = SF_AT(d.t_dmg, last);
-        SF_AT(d.t_pidx, q) = SF_AT(d.t_pidx, last);
+        SF_T(d.t_cell, q) = SF_T(d.t_cell, last);
+        SF_T(d.t_dmg, q) = SF_T(d.t_dmg, last);
+        SF_T(d.t_pidx, q) = SF_T(d.t_pidx, last);
     }
     e.ntemp = last;
 }
 SF_FN bool sf_push_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, int cell, int pidx)
 {
     if ((int)e.ntemp >= k.cap_t) { /* harness: temp.size() > cap is SF_OVERFLOW */
-        e.status = SF_OVERFLOW;
+        sf_fail_env(e, SF_OVERFLOW);
         return false;
     }
-    SF_AT(d.t_cell, e.ntemp) = (uint16_t)cell;
-    SF_AT(d.t_dmg, e.ntemp) = 0;
-    SF_AT(d.t_pidx, e.ntemp) = (uint8_t)pidx;
+    SF_T(d.t_cell, e.ntemp) = (uint16_t)cell;
+    SF_T(d.t_dmg, e.ntemp) = 0;
+    SF_T(d.t_pidx, e.ntemp) = (uint8_t)pidx;
     e.ntemp += 1;
     return true;
 }
@@ -304,56 +342,50 @@ SF_FN int sf_exit_cell(const SfDev &d, const SfConst &k, int env, int idx)
 
 /* ------------------------------------------------------------------ spawns */
 
-/* spawn_chest, gameplay.hpp:532-542 */
-SF_FN void sf_spawn_chest(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+/* spawn_chest / spawn_zombie_npc / spawn_human_npc, gameplay.hpp:532-572 (Zombie::gen_npc
+ * Character.hpp:850-857).  The three share their first three draws (floor, row, col) and the
+ * "cell prints '.'" test, so they run as three rounds of one code path. */
+SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
-    if (9000 <= e.chest) return; /* C, gameplay.hpp:37 */
-    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
-    int cell = sf_cell_of(i, j, c);
-    uint32_t g = SF_G(cell);
-    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
-    int type = sf_rand(e, t) % 4;
-    SF_G(cell) = (uint16_t)((K_CHEST0 + type) << C_KIND_SHIFT);
-    e.chest += 1;
-    if (e.chest > k.cap_chest) e.status = SF_OVERFLOW;
-}
-
-/* spawn_zombie_npc, gameplay.hpp:544-557 with Zombie::gen_npc, Character.hpp:850-857 */
-SF_FN void sf_spawn_zombie(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
-{
-    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
-    int cell = sf_cell_of(i, j, c);
-    uint32_t g = SF_G(cell);
-    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
-    int z = m2_lowest_free(e.mz);
-    if (z >= k.cap_z) {
-        e.status = SF_OVERFLOW;
-        return;
+    for (int kind = 0; kind < 3; ++kind) {
+        uint32_t period = kind == 0 ? 30u : kind == 1 ? 40u : 50u; /* pc, pz, ph: gameplay.hpp:459 */
+        bool due = e.on && (e.frame % period <= 1u);
+        if (kind == 0 && 9000 <= e.chest) due = false; /* C, gameplay.hpp:37 */
+        if (due) {
+            int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
+            int cell = sf_cell_of(i, j, c);
+            uint32_t g = SF_G(cell);
+            if (sf_showit(t.smap[cell], g) == SH_DOT) {
+                if (kind == 0) {
+                    int type = sf_rand(e, t) % 4;
+                    SF_G(cell) = (uint16_t)((K_CHEST0 + type) << C_KIND_SHIFT);
+                    e.chest += 1;
+                    if (e.chest > k.cap_chest) sf_fail_env(e, SF_OVERFLOW);
+                } else if (kind == 1) {
+                    int z = m2_lowest_free(e.mz);
+                    if (z >= k.cap_z) sf_fail_env(e, SF_OVERFLOW);
+                    else {
+                        int super_ = (sf_rand(e, t) % 4 == 0);
+                        SF_AT(d.z_pos, z) = (uint16_t)(cell | (super_ << POS_HI_SHIFT));
+                        SF_AT(d.z_hp, z) = (super_ + 1) * 400;
+                        SF_AT(d.z_mind, z) = (super_ + 1) * 100;
+                        SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
+                        m2_set(e.mz, z);
+                    }
+                } else {
+                    int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
+                    if (h < 0 || h >= k.cap_h) sf_fail_env(e, SF_OVERFLOW);
+                    else {
+                        sf_init_human(d, env, k.npc, h, cell, true, 0, false);
+                        SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)h);
+                        e.mh |= 1ull << h;
+                        if (h + 1 > e.hw_h) e.hw_h = h + 1;
+                    }
+                }
+            }
+        }
+        SF_SYNCWARP();
     }
-    int super_ = (sf_rand(e, t) % 4 == 0);
-    SF_AT(d.z_pos, z) = (uint16_t)(cell | (super_ << POS_HI_SHIFT));
-    SF_AT(d.z_hp, z) = (super_ + 1) * 400;
-    SF_AT(d.z_mind, z) = (super_ + 1) * 100;
-    SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
-    m2_set(e.mz, z);
-}
-
-/* spawn_human_npc, gameplay.hpp:559-572 */
-SF_FN void sf_spawn_human(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
-{
-    int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
-    int cell = sf_cell_of(i, j, c);
-    uint32_t g = SF_G(cell);
-    if (sf_showit(t.smap[cell], g) != SH_DOT) return;
-    int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
-    if (h < 0 || h >= k.cap_h) {
-        e.status = SF_OVERFLOW;
-        return;
-    }
-    sf_init_human(d, env, k.npc, h, cell, true, 0, false);
-    SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)h);
-    e.mh |= 1ull << h;
-    if (h + 1 > e.hw_h) e.hw_h = h + 1;
 }
 
 /* ------------------------------------------------------------------ half-tick pieces */
@@ -361,55 +393,69 @@ SF_FN void sf_spawn_human(const SfDev &d, const SfConst &k, const SfTabs &t, int
 /* zombie_action, gameplay.hpp:654-693 */
 SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
-    int hi = m2_highest(e.mz);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mz) : -1);
     for (int z = 0; z <= hi; ++z) {
-        if (!m2_test(e.mz, z)) continue;
-        uint32_t pw = SF_AT(d.z_pos, z);
-        int cell = (int)(pw & POS_CELL);
-        uint32_t g = SF_G(cell);
-        if (g & C_S2) continue;
-        bool adjacent = false;
-SF_UNROLL
-        for (int i1 = 0; i1 < 4; ++i1) {
-            int nc = cell + sf_delta(i1);
-            uint32_t gn = SF_G(nc);
-            if (gn & C_S0) {
-                if (!(gn & C_S2)) {
-                    int b = sf_alloc_bullet(k, e);
-                    if (b < 0) return;
-                    int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
-                    sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+        bool act = e.on && m2_test(e.mz, z);
+        uint32_t pw = 0, g = 0;
+        int cell = 0;
+        if (act) {
+            pw = SF_AT(d.z_pos, z);
+            cell = (int)(pw & POS_CELL);
+            g = SF_G(cell);
+            act = !(g & C_S2);
+        }
+        bool wander = false;
+        if (act) {
+            bool adjacent = false;
+            SF_UNROLL
+            for (int i1 = 0; i1 < 4; ++i1) {
+                int nc = cell + sf_delta(i1);
+                uint32_t gn = SF_G(nc);
+                if (gn & C_S0) {
+                    adjacent = true;
+                    if (!(gn & C_S2) && e.on) {
+                        int b = sf_alloc_bullet(k, e);
+                        if (b >= 0) {
+                            int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
+                            sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+                        }
+                    }
                 }
-                adjacent = true;
             }
+            wander = !adjacent && e.on;
         }
-        if (adjacent) continue;
-        if (sf_rand(e, t) % 5 < 2) continue;
+        if (wander) wander = !(sf_rand(e, t) % 5 < 2);
         for (int i1 = 0; i1 < 2; ++i1) {
-            int i2 = sf_rand(e, t) % 4;
-            int nc = cell + sf_delta(i2);
-            uint32_t gn = SF_G(nc);
-            if (sf_showit(t.smap[nc], gn) == SH_DOT) {
-                SF_G(nc) = (uint16_t)(C_S1 | (uint32_t)z);
-                SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
-                SF_AT(d.z_pos, z) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
-                break;
+            if (wander) {
+                int i2 = sf_rand(e, t) % 4;
+                int nc = cell + sf_delta(i2);
+                uint32_t gn = SF_G(nc);
+                if (sf_showit(t.smap[nc], gn) == SH_DOT) {
+                    SF_G(nc) = (uint16_t)(C_S1 | (uint32_t)z);
+                    SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
+                    SF_AT(d.z_pos, z) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
+                    wander = false;
+                }
             }
         }
+        SF_SYNCWARP();
     }
 }
 
 /* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates */
 SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
-    for (int i = m2_next(e.mp, 0); i >= 0; i = m2_next(e.mp, i + 1)) {
-        int cell = sf_exit_cell(d, k, env, i);
-        uint32_t g = SF_G(cell);
-        if (g & (C_S0 | C_S1 | C_S2)) {
-            int b = sf_alloc_bullet(k, e);
-            if (b < 0) return;
-            sf_place_bullet(d, env, e, b, cell, g, 2, 1, -1, 20, -10);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mp) : -1);
+    for (int i = 0; i <= hi; ++i) {
+        if (e.on && m2_test(e.mp, i)) {
+            int cell = sf_exit_cell(d, k, env, i);
+            uint32_t g = SF_G(cell);
+            if (g & (C_S0 | C_S1 | C_S2)) {
+                int b = sf_alloc_bullet(k, e);
+                if (b >= 0) sf_place_bullet(d, env, e, b, cell, g, 2, 1, -1, 20, -10);
+            }
         }
+        SF_SYNCWARP();
     }
 }
 
@@ -417,55 +463,59 @@ SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, int cell)
 {
     int q = sf_find_built(d, env, e, cell);
-    if (q < 0) return;
-    uint32_t g = SF_G(cell);
-    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-    int dmg = SF_AT(d.t_dmg, q);
-    if (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)) && dmg >= 1000) { /* lim_portal */
-        int pi = SF_AT(d.t_pidx, q);
-        int ecell = sf_exit_cell(d, k, env, pi);
-        SF_G(ecell) = (uint16_t)(SF_G(ecell) & ~C_KIND);
-        SF_G(cell) = (uint16_t)(g & ~C_KIND);
-        m2_clear(e.mp, pi);
-        sf_remove_built(d, env, e, q);
-        int q1 = sf_find_built(d, env, e, ecell);
-        if (q1 >= 0) sf_remove_built(d, env, e, q1);
-    } else if (kind == K_BLOCK && dmg >= 1100) { /* lim_block */
-        SF_G(cell) = (uint16_t)(g & ~C_KIND);
-        sf_remove_built(d, env, e, q);
+    if (q >= 0) {
+        uint32_t g = SF_G(cell);
+        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+        int dmg = SF_T(d.t_dmg, q);
+        if (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)) && dmg >= 1000) { /* lim_portal */
+            int pi = SF_T(d.t_pidx, q);
+            int ecell = sf_exit_cell(d, k, env, pi);
+            SF_G(ecell) = (uint16_t)(SF_G(ecell) & ~C_KIND);
+            SF_G(cell) = (uint16_t)(g & ~C_KIND);
+            m2_clear(e.mp, pi);
+            sf_remove_built(d, env, e, q);
+            int q1 = sf_find_built(d, env, e, ecell);
+            if (q1 >= 0) sf_remove_built(d, env, e, q1);
+        } else if (kind == K_BLOCK && dmg >= 1100) { /* lim_block */
+            SF_G(cell) = (uint16_t)(g & ~C_KIND);
+            sf_remove_built(d, env, e, q);
+        }
     }
 }
 
 /* update_tmp, gameplay.hpp:1343-1381 */
 SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
-    if (e.ntemp == 0) return; /* nothing player-built: no bullet can be absorbed */
+    const bool any = e.on && e.ntemp != 0; /* nothing player-built: no bullet can be absorbed */
+    const int hi = SF_WARP_MAX(any ? m2_highest(e.mb) : -1);
     int hit_cell[4];
     int n_hit = 0;
-    bool many = false;
-    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
-        int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
-        uint32_t g = SF_G(cell);
-        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-        if (kind == K_BLOCK || (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)))) {
-            int q = sf_find_built(d, env, e, cell);
-            SF_AT(d.t_dmg, q) += SF_AT(d.b_dmg, b);
-            SF_G(cell) = (uint16_t)(g & ~C_S2);
-            m2_clear(e.mb, b);
-            if (n_hit < 4) hit_cell[n_hit++] = cell;
-            else many = true;
+    for (int b = 0; b <= hi; ++b) {
+        if (any && m2_test(e.mb, b)) {
+            int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
+            uint32_t g = SF_G(cell);
+            uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+            if (kind == K_BLOCK || (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)))) {
+                int q = sf_find_built(d, env, e, cell);
+                SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b);
+                SF_G(cell) = (uint16_t)(g & ~C_S2);
+                m2_clear(e.mb, b);
+                if (n_hit < 4) hit_cell[n_hit] = cell;
+                n_hit += 1;
+            }
         }
+        SF_SYNCWARP();
     }
     /* a limit can only be crossed by an absorption of this very call (while a human hides an
      * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
-    if (many) {
-        for (int q = (int)e.ntemp - 1; q >= 0; --q) {
-            if (q >= (int)e.ntemp) continue;
-            sf_check_built(d, k, env, e, SF_AT(d.t_cell, q));
-        }
+    if (n_hit > 4) {
+        for (int q = (int)e.ntemp - 1; q >= 0; --q)
+            if (q < (int)e.ntemp) sf_check_built(d, k, env, e, SF_T(d.t_cell, q));
     } else {
-        for (int i = 0; i < n_hit; ++i) sf_check_built(d, k, env, e, hit_cell[i]);
+        for (int i = 0; i < 4; ++i)
+            if (i < n_hit) sf_check_built(d, k, env, e, hit_cell[i]);
     }
+    SF_SYNCWARP();
 }
 
 /* human_damage, gameplay.hpp:611-634 */
@@ -534,29 +584,38 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
  * bullets, credits are sums), so their order does not matter. */
 SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
 {
-    uint64_t q = e.quit & e.mh; /* first branch of hit_human: Hp <= 0 without a bullet test */
+    uint64_t q = e.on ? (e.quit & e.mh) : 0ull; /* first branch of hit_human: Hp <= 0, no bullet test */
     e.quit = 0;
-    while (q) {
-        int h = sf_ffs64(q);
-        q &= q - 1;
-        e.mh &= ~(1ull << h);
-        if (h != 0) {
-            int cell = (int)(SF_AT(d.h_pw, h) & POS_CELL);
-            SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
-            SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT);
+    const int nq = SF_WARP_MAX(sf_popc64(q));
+    for (int i = 0; i < nq; ++i) {
+        if (q) {
+            int h = sf_ffs64(q);
+            q &= q - 1;
+            e.mh &= ~(1ull << h);
+            if (h != 0) {
+                int cell = (int)(SF_AT(d.h_pw, h) & POS_CELL);
+                SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
+                SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT);
+            }
         }
+        SF_SYNCWARP();
     }
-    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
-        uint32_t meta = SF_AT(d.b_meta, b);
-        if (!(meta & BF_OWNS)) continue;
-        int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
-        uint32_t g = SF_G(cell);
-        if (g & C_S0) {
-            int h = (int)(g & C_OCC);
-            if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b, cell, g, meta);
-        } else if (g & C_S1) {
-            sf_zombie_damage(d, env, e, (int)(g & C_OCC), b, cell, g, meta);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
+    for (int b = 0; b <= hi; ++b) {
+        if (e.on && m2_test(e.mb, b)) {
+            uint32_t meta = SF_AT(d.b_meta, b);
+            if (meta & BF_OWNS) {
+                int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
+                uint32_t g = SF_G(cell);
+                if (g & C_S0) {
+                    int h = (int)(g & C_OCC);
+                    if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b, cell, g, meta);
+                } else if (g & C_S1) {
+                    sf_zombie_damage(d, env, e, (int)(g & C_OCC), b, cell, g, meta);
+                }
+            }
         }
+        SF_SYNCWARP();
     }
 }
 
@@ -566,65 +625,82 @@ SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
  * a cell here is the reference's last writer of it. */
 SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
 {
-    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
-        uint32_t pw = SF_AT(d.b_pw, b);
-        int cell = (int)(pw & POS_CELL), nc;
-        if (!sf_neighbour(cell, (int)(pw >> POS_HI_SHIFT), &nc)) {
-            e.status = SF_UB_GUARD; /* the reference would read themap[i][-1][k], :1069 */
-            return;
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
+    bool oob = false;
+    for (int b = 0; b <= hi; ++b) {
+        if (e.on && m2_test(e.mb, b)) {
+            uint32_t pw = SF_AT(d.b_pw, b);
+            int nc;
+            if (!sf_neighbour((int)(pw & POS_CELL), (int)(pw >> POS_HI_SHIFT), &nc)) oob = true;
         }
     }
-    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
-        uint32_t pw = SF_AT(d.b_pw, b);
-        int cell = (int)(pw & POS_CELL);
-        int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
-        uint32_t g = SF_G(cell);
-        if (g & C_S2) SF_G(cell) = (uint16_t)(g & ~C_S2);
-        uint32_t gn = SF_G(nc);
-        if (gn & C_S2) SF_G(nc) = (uint16_t)(gn & ~C_S2);
-    }
-    int r = sf_rand(e, t) & 1;
-    /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
-    int b = r ? m2_prev(e.mb, 127) : m2_next(e.mb, 0);
-    while (b >= 0) {
-        uint32_t pw = SF_AT(d.b_pw, b);
-        uint32_t meta = SF_AT(d.b_meta, b) & ~BF_OWNS;
-        int cell = (int)(pw & POS_CELL);
-        uint32_t range = meta & 0xFFu, trav = (meta >> 8) & 0xFFu;
-        if (trav + 1 >= range) { /* Bullet::expire, Item.hpp:165-168 */
-            m2_clear(e.mb, b);
-        } else {
+    if (oob) sf_fail_env(e, SF_UB_GUARD); /* the reference would read themap[i][-1][k], :1069 */
+    SF_SYNCWARP();
+    for (int b = 0; b <= hi; ++b) {
+        if (e.on && m2_test(e.mb, b)) {
+            uint32_t pw = SF_AT(d.b_pw, b);
+            int cell = (int)(pw & POS_CELL);
             int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
+            uint32_t g = SF_G(cell);
+            if (g & C_S2) SF_G(cell) = (uint16_t)(g & ~C_S2);
             uint32_t gn = SF_G(nc);
-            int sit = sf_showit(t.smap[nc], gn);
-            bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
-            if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
-                if (!(gn & C_S2)) meta |= BF_OWNS;
-                SF_G(nc) = (uint16_t)(gn | C_S2);
-                SF_AT(d.b_pw, b) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
-                SF_AT(d.b_meta, b) = meta + 0x100u;
-            } else {
+            if (gn & C_S2) SF_G(nc) = (uint16_t)(gn & ~C_S2);
+        }
+        SF_SYNCWARP();
+    }
+    int r = 0;
+    if (e.on) r = sf_rand(e, t) & 1;
+    SF_SYNCWARP();
+    /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
+    for (int i = 0; i <= hi; ++i) {
+        int b = r ? hi - i : i;
+        if (e.on && m2_test(e.mb, b)) {
+            uint32_t pw = SF_AT(d.b_pw, b);
+            uint32_t meta = SF_AT(d.b_meta, b) & ~BF_OWNS;
+            int cell = (int)(pw & POS_CELL);
+            uint32_t range = meta & 0xFFu, trav = (meta >> 8) & 0xFFu;
+            if (trav + 1 >= range) { /* Bullet::expire, Item.hpp:165-168 */
                 m2_clear(e.mb, b);
+            } else {
+                int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
+                uint32_t gn = SF_G(nc);
+                int sit = sf_showit(t.smap[nc], gn);
+                bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
+                if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
+                    if (!(gn & C_S2)) meta |= BF_OWNS;
+                    SF_G(nc) = (uint16_t)(gn | C_S2);
+                    SF_AT(d.b_pw, b) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
+                    SF_AT(d.b_meta, b) = meta + 0x100u;
+                } else {
+                    m2_clear(e.mb, b);
+                }
             }
         }
-        b = r ? m2_prev(e.mb, b - 1) : m2_next(e.mb, b + 1);
+        SF_SYNCWARP();
     }
 }
 
-/* human_rnpc_bot, gameplay.hpp:1927-1940; returns the command symbol */
-SF_FN int sf_rnpc_bot(const SfTabs &t, SfEnv &e)
+/* human_rnpc_bot, gameplay.hpp:1927-1940; returns the command symbol.  Written as a chain of
+ * "does this lane still need a draw" steps so that the lanes of a warp stay together. */
+SF_FN int sf_rnpc_bot(const SfTabs &t, SfEnv &e, bool want)
 {
-    if (e.frame % 50 <= 1) {
-        const char c[8] = {'c', 'v', 'b', 'n', 'm', ',', '.', '/'};
-        return c[sf_rand(e, t) % 8];
+    int c = '+';
+    bool pick_weapon = want && (e.frame % 50 <= 1);
+    bool more = want && !pick_weapon;
+    if (pick_weapon) {
+        const char w[8] = {'c', 'v', 'b', 'n', 'm', ',', '.', '/'};
+        c = w[sf_rand(e, t) % 8];
     }
-    if (sf_rand(e, t) % 5 < 3) return 'x';
-    if (sf_rand(e, t) % 5 < 3) {
-        const char c[7] = {'1', '2', 'a', 'w', 's', 'd', 'p'};
-        return c[sf_rand(e, t) % 7];
+    if (more && sf_rand(e, t) % 5 < 3) c = 'x', more = false;
+    bool second = false;
+    if (more) second = sf_rand(e, t) % 5 < 3;
+    if (more) {
+        int r = sf_rand(e, t);
+        const char a[7] = {'1', '2', 'a', 'w', 's', 'd', 'p'};
+        const char o[8] = {'+', 'u', 'f', 'g', 'h', 'j', '[', ']'};
+        c = second ? a[r % 7] : o[r % 8];
     }
-    const char c[8] = {'+', 'u', 'f', 'g', 'h', 'j', '[', ']'};
-    return c[sf_rand(e, t) % 8];
+    return c;
 }
 
 /* index of a selection key in its row, -1 if c is not in it (obey, gameplay.hpp:759-791) */
@@ -653,26 +729,24 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                 uint32_t bp = SF_AT(d.h_bp, h);
                 uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
                 if (c == '[') {
-                    if (blocks) {
-                        if (!sf_push_built(d, k, env, e, nc, 0)) return;
+                    if (blocks && sf_push_built(d, k, env, e, nc, 0)) {
                         SF_G(nc) = (uint16_t)(K_BLOCK << C_KIND_SHIFT);
                         SF_AT(d.h_bp, h) = bp - 1u;
                     }
                 } else if (pend) { /* second press: the entrance bound to the pending exit */
-                    if (!sf_push_built(d, k, env, e, nc, (int)pend - 1)) return;
-                    SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
-                    SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
+                    if (sf_push_built(d, k, env, e, nc, (int)pend - 1)) {
+                        SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
+                        SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
+                    }
                 } else if (portals) { /* first press: the exit, lowest free portal slot (p_ind) */
                     int pi = m2_lowest_free(e.mp);
-                    if (pi >= k.cap_p) {
-                        e.status = SF_OVERFLOW;
-                        return;
+                    if (pi >= k.cap_p) sf_fail_env(e, SF_OVERFLOW);
+                    else if (sf_push_built(d, k, env, e, nc, 0)) {
+                        SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
+                        SF_AT(d.p_cell, pi) = (uint16_t)nc;
+                        m2_set(e.mp, pi);
+                        SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);
                     }
-                    if (!sf_push_built(d, k, env, e, nc, 0)) return;
-                    SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
-                    SF_AT(d.p_cell, pi) = (uint16_t)nc;
-                    m2_set(e.mp, pi);
-                    SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);
                 }
             }
         }
@@ -714,7 +788,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         if (sf_neighbour(cell, way0, &nc)) {
             uint32_t sel = SF_AT(d.h_sel, h);
             int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
-            bool can = false, fire = true;
+            bool can = false;
             int dmg = 0, eff = 0, range = 1;
             if (c == 'z') { /* Human::punch, Character.hpp:391-397 */
                 int md = SF_AT(d.h_mind, h), pb = sf_punch_base(k, e, h);
@@ -748,19 +822,17 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                     eff = w.effect, range = w.range;
                     can = true;
                 }
-            } else
-                fire = false;
-            if (fire && can) {
+            }
+            if (can) {
                 uint32_t gn = SF_G(nc);
                 int sit = sf_showit(t.smap[nc], gn);
                 bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
                 if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
-                    if (b >= k.cap_b) {
-                        e.status = SF_OVERFLOW;
-                        return;
+                    if (b >= k.cap_b) sf_fail_env(e, SF_OVERFLOW);
+                    else {
+                        m2_set(e.mb, b);
+                        sf_place_bullet(d, env, e, b, nc, gn, way0, range, h, dmg, eff);
                     }
-                    m2_set(e.mb, b);
-                    sf_place_bullet(d, env, e, b, nc, gn, way0, range, h, dmg, eff);
                 }
             }
         }
@@ -783,33 +855,34 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             }
         }
     }
-    if (e.status != SF_RUNNING) return;
-    /* teleport, gameplay.hpp:517-530 */
-    uint32_t g = SF_G(cell);
-    uint32_t st = t.smap[cell];
-    int pidx = -1;
-    if (st & (M_UP | M_DOWN)) pidx = (int)(st >> M_TARGET_SHIFT);
-    else if (((g >> C_KIND_SHIFT) & 7u) == K_ENTRANCE) pidx = SF_AT(d.t_pidx, sf_find_built(d, env, e, cell));
-    if (pidx >= 0) {
-        int dc = sf_exit_cell(d, k, env, pidx);
-        uint32_t gd = SF_G(dc);
-        if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
-            SF_G(dc) = (uint16_t)((gd & ~C_OCC) | C_S0 | (uint32_t)h);
-            SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
-            cell = dc;
-            SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
-            g = SF_G(cell);
+    if (e.on) {
+        /* teleport, gameplay.hpp:517-530 */
+        uint32_t g = SF_G(cell);
+        uint32_t st = t.smap[cell];
+        int pidx = -1;
+        if (st & (M_UP | M_DOWN)) pidx = (int)(st >> M_TARGET_SHIFT);
+        else if (((g >> C_KIND_SHIFT) & 7u) == K_ENTRANCE) pidx = SF_T(d.t_pidx, sf_find_built(d, env, e, cell));
+        if (pidx >= 0) {
+            int dc = sf_exit_cell(d, k, env, pidx);
+            uint32_t gd = SF_G(dc);
+            if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
+                SF_G(dc) = (uint16_t)((gd & ~C_OCC) | C_S0 | (uint32_t)h);
+                SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
+                cell = dc;
+                SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
+                g = SF_G(cell);
+            }
         }
-    }
-    /* claim_chest, gameplay.hpp:507-515, Human::claim_chest Character.hpp:372-377 */
-    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-    if (kind >= K_CHEST0 && kind < K_BLOCK) {
-        int ty = (int)kind - K_CHEST0;
-        SF_AT(d.h_stam, h) += k.cons[ty].stamina;
-        SF_AT(d.h_hp, h) += k.cons[ty].hp;
-        SF_AT(d.h_mind, h) += k.cons[ty].effect;
-        SF_G(cell) = (uint16_t)(g & ~C_KIND);
-        e.chest -= 1;
+        /* claim_chest, gameplay.hpp:507-515, Human::claim_chest Character.hpp:372-377 */
+        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+        if (kind >= K_CHEST0 && kind < K_BLOCK) {
+            int ty = (int)kind - K_CHEST0;
+            SF_AT(d.h_stam, h) += k.cons[ty].stamina;
+            SF_AT(d.h_hp, h) += k.cons[ty].hp;
+            SF_AT(d.h_mind, h) += k.cons[ty].effect;
+            SF_G(cell) = (uint16_t)(g & ~C_KIND);
+            e.chest -= 1;
+        }
     }
 }
 
@@ -820,28 +893,32 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
                            const uint8_t *actions)
 {
     uint8_t cmd[SF_LIM_HUMANS];
-    uint64_t live = e.mh;
-    cmd[0] = actions ? actions[0] : (uint8_t)'+';
-    for (uint64_t m = live & ~1ull; m; m &= m - 1) {
-        int h = sf_ffs64(m);
-        uint32_t sel = SF_AT(d.h_sel, h);
-        int c = '+';
-        if (sel & HS_RNPC) c = sf_rnpc_bot(t, e);
-        else if ((sel & HS_AGENT) && h < k.n_agents && actions) {
-            c = actions[h];
-            bool ok = c == '+' || c == 'x' || c == 'z' || c == 'q' || c == 'e' || c == 'a' || c == 'w' || c == 's' ||
-                      c == 'd';
-            if (!ok) c = '+';
+    const uint64_t live = e.on ? e.mh : 0ull;
+    const int hi = SF_WARP_MAX(live ? sf_fls64(live) : -1);
+    cmd[0] = (actions && e.on) ? actions[0] : (uint8_t)'+';
+    for (int h = 1; h <= hi; ++h) {
+        bool is_live = (live >> h) & 1;
+        uint32_t sel = is_live ? SF_AT(d.h_sel, h) : 0u;
+        int c = sf_rnpc_bot(t, e, is_live && (sel & HS_RNPC));
+        if (is_live && !(sel & HS_RNPC)) {
+            c = '+';
+            if ((sel & HS_AGENT) && h < k.n_agents && actions) {
+                c = actions[h];
+                bool ok = c == '+' || c == 'x' || c == 'z' || c == 'q' || c == 'e' || c == 'a' || c == 'w' ||
+                          c == 's' || c == 'd';
+                if (!ok) c = '+';
+            }
         }
         cmd[h] = (uint8_t)c;
+        SF_SYNCWARP();
     }
-    int r = sf_rand(e, t) & 1;
-    uint64_t m = live;
-    while (m) {
-        int h = r ? sf_ffs64(m) : sf_fls64(m);
-        m &= ~(1ull << h);
-        sf_obey(d, k, t, env, e, h, cmd[h]);
-        if (e.status != SF_RUNNING) return;
+    int r = 0;
+    if (e.on) r = sf_rand(e, t) & 1;
+    SF_SYNCWARP();
+    for (int i = 0; i <= hi; ++i) {
+        int h = r ? i : hi - i;
+        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, cmd[h]);
+        SF_SYNCWARP();
     }
 }
 
@@ -872,6 +949,7 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
     e.kills = e.tkills = e.loot = e.chest = 0;
     e.ntemp = 0;
     e.status = SF_RUNNING;
+    e.on = true;
     e.quit = 0;
     e.mz[0] = e.mz[1] = e.mb[0] = e.mb[1] = 0;
     e.mp[0] = (1ull << k.n_static_exits) - 1ull;
@@ -903,44 +981,38 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
  * end of the step, wall clock replaced by the frame clock (level * 300 s = level * 7500 frames) */
 SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
-    if (e.status != SF_RUNNING) return;
-    if (SF_AT(d.h_hp, 0) <= 0) {
-        e.status = SF_DEAD;
-        return;
-    }
-    if (k.mode == SF_MODE_TIMER) {
-        if ((int64_t)e.frame >= (int64_t)e.level * 7500) e.status = (e.kills < e.level * 5) ? SF_TIMEOUT : SF_WIN;
-    } else if (k.mode == SF_MODE_SOLO) {
-        if (e.level * 5 <= e.kills) e.status = SF_WIN;
-    } else if (e.level * 10 <= e.tkills) {
-        /* rivals_are_dead, gameplay.hpp:497-505 */
-        uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
-        bool alive = false;
-        for (uint64_t m = e.mh; m; m &= m - 1) {
-            uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
-            if (tm && tm != me) alive = true;
+    if (e.on) {
+        if (SF_AT(d.h_hp, 0) <= 0) {
+            e.status = SF_DEAD;
+        } else if (k.mode == SF_MODE_TIMER) {
+            if ((int64_t)e.frame >= (int64_t)e.level * 7500) e.status = (e.kills < e.level * 5) ? SF_TIMEOUT : SF_WIN;
+        } else if (k.mode == SF_MODE_SOLO) {
+            if (e.level * 5 <= e.kills) e.status = SF_WIN;
+        } else if (e.level * 10 <= e.tkills) {
+            /* rivals_are_dead, gameplay.hpp:497-505 */
+            uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
+            bool alive = false;
+            for (uint64_t m = e.mh; m; m &= m - 1) {
+                uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
+                if (tm && tm != me) alive = true;
+            }
+            if (!alive) e.status = SF_WIN;
         }
-        if (!alive) e.status = SF_WIN;
+        if (e.status == SF_RUNNING && k.max_steps > 0 && (int)e.steps >= k.max_steps) e.status = SF_TRUNCATED;
+        e.on = e.status == SF_RUNNING;
     }
-    if (e.status == SF_RUNNING && k.max_steps > 0 && (int)e.steps >= k.max_steps) e.status = SF_TRUNCATED;
+    SF_SYNCWARP();
 }
 
 /* first half of the loop body: spawns and half-tick A, gameplay.hpp:1444-1461 */
 SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
-    if (e.frame % 30 <= 1) sf_spawn_chest(d, k, t, env, e);   /* pc, gameplay.hpp:459 */
-    if (e.status != SF_RUNNING) return;
-    if (e.frame % 40 <= 1) sf_spawn_zombie(d, k, t, env, e);  /* pz */
-    if (e.status != SF_RUNNING) return;
-    if (e.frame % 50 <= 1) sf_spawn_human(d, k, t, env, e);   /* ph */
-    if (e.status != SF_RUNNING) return;
+    sf_spawns(d, k, t, env, e);
     sf_zombie_action(d, k, t, env, e);
-    if (e.status != SF_RUNNING) return;
     sf_portal_damage(d, k, env, e);
-    if (e.status != SF_RUNNING) return;
     sf_update_tmp(d, k, env, e);
     sf_hits(d, env, e);
-    e.frame += 1;
+    if (e.on) e.frame += 1;
     sf_update_bull(d, t, env, e);
 }
 
@@ -948,13 +1020,11 @@ SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
 SF_FN void sf_step_b(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, const uint8_t *actions)
 {
     sf_human_action(d, k, t, env, e, actions);
-    if (e.status != SF_RUNNING) return;
     sf_update_tmp(d, k, env, e);
     sf_hits(d, env, e);
-    e.frame += 1;
+    if (e.on) e.frame += 1;
     sf_update_bull(d, t, env, e);
-    if (e.status != SF_RUNNING) return;
-    e.steps += 1;
+    if (e.on) e.steps += 1;
     sf_eval_end(d, k, env, e);
 }
 
@@ -972,13 +1042,14 @@ SF_FN void sf_load_env(const SfDev &d, int env, SfEnv &e)
     e.mb[0] = SF_AT(d.mb, 0), e.mb[1] = SF_AT(d.mb, 1);
     e.mp[0] = SF_AT(d.mp, 0), e.mp[1] = SF_AT(d.mp, 1);
     e.quit = 0;
-SF_UNROLL
+    SF_UNROLL
     for (int i = 0; i < 18; ++i) {
         e.L[i] = SF_AT(d.rng_log, i);
         e.cst[i] = SF_AT(d.rng_cst, i);
     }
     e.jomle = d.jomle[env];
     e.draws = 0;
+    e.on = e.status == SF_RUNNING;
 }
 
 SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e, bool store_cst)
@@ -991,7 +1062,7 @@ SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e, bool store_cst)
     SF_AT(d.mz, 0) = e.mz[0], SF_AT(d.mz, 1) = e.mz[1];
     SF_AT(d.mb, 0) = e.mb[0], SF_AT(d.mb, 1) = e.mb[1];
     SF_AT(d.mp, 0) = e.mp[0], SF_AT(d.mp, 1) = e.mp[1];
-SF_UNROLL
+    SF_UNROLL
     for (int i = 0; i < 18; ++i) {
         SF_AT(d.rng_log, i) = (uint16_t)e.L[i];
         if (store_cst) SF_AT(d.rng_cst, i) = e.cst[i];
@@ -1008,7 +1079,6 @@ SF_FN uint32_t sf_algo_bytes(const SfConst &k, const SfEnv &e)
     return 2u * (140u + 64u * nh + 12u * nz + 28u * nb + 4u * (uint32_t)e.chest + 8u * e.ntemp + 4u * np) +
            (uint32_t)k.n_agents + 32u;
 }
-
 
 /* ------------------------------------------------------------------ kernel bodies */
 
@@ -1036,53 +1106,58 @@ SF_FN void sf_reset_body(const SfDev &d, const SfConst &k, const SfTabs &t, int 
 }
 
 /* one env-step (or one half of it) for arena `env`; `actions` is the arena's row of the
- * action buffer (NULL for SF_HALF_A) */
-SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int env, const uint8_t *actions, int half,
-                        SfStatDelta &sd)
+ * action buffer (NULL for SF_HALF_A).  `valid` is false for the padding lanes of the last
+ * warp: they walk through the same code with nothing to do, so that every lane of a warp
+ * reaches every SF_SYNCWARP(). */
+SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int env, bool valid,
+                        const uint8_t *actions, int half, SfStatDelta &sd)
 {
     SfEnv e;
     sf_load_env(d, env, e);
+    if (!valid) e.on = false;
+    const bool was_on = e.on;
     sf_step_out o;
     if (half == SF_HALF_B) o = d.out[env];
     else o.status = 0, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0, o.episode_steps = 0;
-    if (e.status != SF_RUNNING) { /* terminal and not auto-reset: the arena waits for sf_reset */
-        o.status = e.status;
-        o.episode_steps = (int32_t)e.steps;
-        d.out[env] = o;
-        return;
-    }
     int32_t kills0 = e.kills, tkills0 = e.tkills, loot0 = e.loot;
     int32_t hp0 = SF_AT(d.h_hp, 0), dmg0 = SF_AT(d.h_dmg, 0), eff0 = SF_AT(d.h_eff, 0);
     if (half != SF_HALF_B) {
-        sd.algo_bytes += sf_algo_bytes(k, e);
+        if (e.on) sd.algo_bytes += sf_algo_bytes(k, e);
         sf_step_a(d, k, t, env, e);
     }
-    if (half != SF_HALF_A && e.status == SF_RUNNING) sf_step_b(d, k, t, env, e, actions);
-    o.d_kills += e.kills - kills0, o.d_teams_kills += e.tkills - tkills0, o.d_loot += e.loot - loot0;
-    o.d_hp += SF_AT(d.h_hp, 0) - hp0, o.d_damage += SF_AT(d.h_dmg, 0) - dmg0, o.d_effect += SF_AT(d.h_eff, 0) - eff0;
-    o.status = e.status;
-    o.episode_steps = (int32_t)e.steps;
-    d.out[env] = o;
-    sd.kills += e.kills - kills0, sd.tkills += e.tkills - tkills0, sd.loot += e.loot - loot0;
-    sd.draws += e.draws;
-    if (half != SF_HALF_A && (e.status == SF_RUNNING || e.status == SF_WIN || e.status == SF_DEAD ||
-                              e.status == SF_TIMEOUT || e.status == SF_TRUNCATED))
-        sd.steps += 1; /* a step that ran to its end (overflow / guard abort it midway) */
-    if (e.status != SF_RUNNING) {
-        sd.episodes += 1;
-        sd.wins += e.status == SF_WIN, sd.deaths += e.status == SF_DEAD, sd.timeouts += e.status == SF_TIMEOUT;
-        sd.truncated += e.status == SF_TRUNCATED, sd.overflows += e.status == SF_OVERFLOW;
-        sd.ub_guards += e.status == SF_UB_GUARD;
-        if (k.auto_reset) { /* new behaviour: next episode of the synthetic seed chain */
-            int64_t ge = k.env_id_base + env;
-            e.episode += 1;
-            e.draws = 0;
-            sf_reset_env(d, k, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode));
-            sf_store_env(d, env, e, true);
-            return;
-        }
+    if (half != SF_HALF_A) sf_step_b(d, k, t, env, e, actions);
+    if (valid) {
+        /* a terminal arena that is not auto-reset waits for sf_reset: report, change nothing */
+        o.d_kills += e.kills - kills0, o.d_teams_kills += e.tkills - tkills0, o.d_loot += e.loot - loot0;
+        o.d_hp += SF_AT(d.h_hp, 0) - hp0, o.d_damage += SF_AT(d.h_dmg, 0) - dmg0, o.d_effect += SF_AT(d.h_eff, 0) - eff0;
+        o.status = e.status;
+        o.episode_steps = (int32_t)e.steps;
+        d.out[env] = o;
     }
-    sf_store_env(d, env, e, false);
+    bool reset = false;
+    if (was_on) {
+        sd.kills += e.kills - kills0, sd.tkills += e.tkills - tkills0, sd.loot += e.loot - loot0;
+        sd.draws += e.draws;
+        if (half != SF_HALF_A && (e.status == SF_RUNNING || e.status == SF_WIN || e.status == SF_DEAD ||
+                                  e.status == SF_TIMEOUT || e.status == SF_TRUNCATED))
+            sd.steps += 1; /* a step that ran to its end (overflow / guard abort it midway) */
+        if (e.status != SF_RUNNING) {
+            sd.episodes += 1;
+            sd.wins += e.status == SF_WIN, sd.deaths += e.status == SF_DEAD, sd.timeouts += e.status == SF_TIMEOUT;
+            sd.truncated += e.status == SF_TRUNCATED, sd.overflows += e.status == SF_OVERFLOW;
+            sd.ub_guards += e.status == SF_UB_GUARD;
+            reset = k.auto_reset != 0;
+        }
+        if (!reset) sf_store_env(d, env, e, false);
+    }
+    if (reset) { /* new behaviour: next episode of the synthetic seed chain */
+        int64_t ge = k.env_id_base + env;
+        e.episode += 1;
+        e.draws = 0;
+        sf_reset_env(d, k, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode));
+        sf_store_env(d, env, e, true);
+    }
+    SF_SYNCWARP();
 }
 
 #endif /* SF_CORE_CUH */

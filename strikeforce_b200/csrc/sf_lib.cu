@@ -89,8 +89,8 @@ sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *
     memset(&sd, 0, sizeof sd);
     for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
         int env = chunk * 32 + lane;
-        if (env < d.n_envs)
-            sf_step_body(d, k, t, env, actions ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);
+        bool valid = env < d.n_envs;
+        sf_step_body(d, k, t, env, valid, (actions && valid) ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);
     }
     __syncwarp();
     sf_flush_stats(d, sd);
@@ -210,7 +210,7 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             }
         }
     for (int q = threadIdx.x; q < (int)e.ntemp; q += SF_OBS_CTA) {
-        int cell = (int)SF_AT(d.t_cell, q) - fbase;
+        int cell = (int)SF_T(d.t_cell, q) - fbase;
         if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
             int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
             if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN) tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
@@ -310,7 +310,7 @@ void carve(Carver &c, sf_handle &h)
     c.take(d.misc, E), c.take(d.steps, E), c.take(d.episode, E), c.take(d.ntemp, E);
     c.take(d.mh, E), c.take(d.mz, 2 * E), c.take(d.mb, 2 * E), c.take(d.mp, 2 * E);
     c.take(d.rng_log, 18 * E), c.take(d.rng_cst, 18 * E), c.take(d.jomle, E);
-    size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)k.cap_t * E;
+    size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)d.cap_t * E;
     c.take(d.h_pw, H), c.take(d.h_sel, H), c.take(d.h_bp, H), c.take(d.h_hp, H), c.take(d.h_mind, H);
     c.take(d.h_stam, H), c.take(d.h_kills, H), c.take(d.h_dmg, H), c.take(d.h_eff, H), c.take(d.h_cons, H);
     c.take(d.h_thr, H);
@@ -368,6 +368,7 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     memset(&h->d, 0, sizeof h->d);
     h->d.n_envs = cfg->n_envs;
     h->d.E = (cfg->n_envs + 31) / 32 * 32;
+    h->d.cap_t = (h->k.cap_t + 7) / 8 * 8;
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
     int smem_optin = 0;

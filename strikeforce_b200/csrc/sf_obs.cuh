@@ -89,7 +89,7 @@ SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, 
         else if (s1) f[18] = SF_AT(d.z_hp, occ);
         else if (s10) {
             if (tq == -2) tq = sf_find_built(d, env, e, cell);
-            int dmg = tq >= 0 ? SF_AT(d.t_dmg, tq) : 0;
+            int dmg = tq >= 0 ? SF_T(d.t_dmg, tq) : 0;
             f[18] = (s3 ? 1100 : 1000) - dmg; /* lim_block / lim_portal, gameplay.hpp:37 */
         }
     } else if (s7)

@@ -104,6 +104,7 @@ typedef struct SfConst {
 /* device arrays; E = env stride (n_envs rounded up to 32) */
 typedef struct SfDev {
     int32_t n_envs, E;
+    int32_t cap_t;     /* player-built records per arena (multiple of 8) */
     /* header */
     uint32_t *frame;
     int32_t *kills, *tkills, *loot, *chest;
@@ -126,7 +127,7 @@ typedef struct SfDev {
     uint16_t *b_pw;
     uint32_t *b_meta;
     int32_t *b_dmg, *b_eff;
-    /* player-built cells [cap_t][E] (gameplay::temp, gameplay.hpp:469) */
+    /* player-built cells [E][cap_t], contiguous per arena (gameplay::temp, gameplay.hpp:469) */
     uint16_t *t_cell;
     int32_t *t_dmg;
     uint8_t *t_pidx;

@@ -43,13 +43,14 @@ HcHandle *hc_create(const sf_config *cfg)
     const SfConst &k = h->k;
     size_t E = (size_t)((cfg->n_envs + 31) / 32 * 32);
     d.n_envs = cfg->n_envs, d.E = (int32_t)E;
+    d.cap_t = (k.cap_t + 7) / 8 * 8;
     d.frame = h->alloc<uint32_t>(E), d.kills = h->alloc<int32_t>(E), d.tkills = h->alloc<int32_t>(E);
     d.loot = h->alloc<int32_t>(E), d.chest = h->alloc<int32_t>(E), d.misc = h->alloc<uint32_t>(E);
     d.steps = h->alloc<uint32_t>(E), d.episode = h->alloc<uint32_t>(E), d.ntemp = h->alloc<uint32_t>(E);
     d.mh = h->alloc<uint64_t>(E), d.mz = h->alloc<uint64_t>(2 * E), d.mb = h->alloc<uint64_t>(2 * E);
     d.mp = h->alloc<uint64_t>(2 * E);
     d.rng_log = h->alloc<uint16_t>(18 * E), d.rng_cst = h->alloc<uint32_t>(18 * E), d.jomle = h->alloc<uint32_t>(E);
-    size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)k.cap_t * E;
+    size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)d.cap_t * E;
     d.h_pw = h->alloc<uint16_t>(H), d.h_sel = h->alloc<uint16_t>(H), d.h_bp = h->alloc<uint32_t>(H);
     d.h_hp = h->alloc<int32_t>(H), d.h_mind = h->alloc<int32_t>(H), d.h_stam = h->alloc<int32_t>(H);
     d.h_kills = h->alloc<int32_t>(H), d.h_dmg = h->alloc<int32_t>(H), d.h_eff = h->alloc<int32_t>(H);
@@ -100,7 +101,7 @@ void hc_step(HcHandle *h, const uint8_t *actions, int half)
 {
     SfStatDelta sd = {};
     for (int env = 0; env < h->d.n_envs; ++env)
-        sf_step_body(h->d, h->k, h->t, env, actions ? actions + (size_t)env * h->k.n_agents : nullptr, half, sd);
+        sf_step_body(h->d, h->k, h->t, env, true, actions ? actions + (size_t)env * h->k.n_agents : nullptr, half, sd);
     add_stats(h, sd);
 }
 

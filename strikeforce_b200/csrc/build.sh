@@ -4,7 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-OUT="$ROOT/strikeforce_b200/libstrikeforce_b200.so"
+OUT="${SF_OUT:-$ROOT/strikeforce_b200/libstrikeforce_b200.so}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-Wall,-Wno-unused-parameter -shared \
     -I"$ROOT/include" -I"$HERE" ${SF_NVCC_EXTRA:-} \

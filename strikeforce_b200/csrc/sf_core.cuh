@@ -390,51 +390,85 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
 
 /* ------------------------------------------------------------------ half-tick pieces */
 
-/* zombie_action, gameplay.hpp:654-693 */
+/* zombie_action, gameplay.hpp:654-693.  Two zombies per round: their positions, then their own
+ * cell and four neighbours, are loaded back to back (ten independent loads in flight) before
+ * the rules run in slot order; what the first zombie writes is forwarded into the second
+ * zombie's loaded copy so that it sees exactly what a sequential walk would. */
 SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mz) : -1);
-    for (int z = 0; z <= hi; ++z) {
-        bool act = e.on && m2_test(e.mz, z);
-        uint32_t pw = 0, g = 0;
-        int cell = 0;
-        if (act) {
-            pw = SF_AT(d.z_pos, z);
-            cell = (int)(pw & POS_CELL);
-            g = SF_G(cell);
-            act = !(g & C_S2);
+    for (int z0 = 0; z0 <= hi; z0 += 2) {
+        bool act[2];
+        uint32_t pw[2];
+        int cell[2];
+        uint32_t gv[2][5];
+        SF_UNROLL
+        for (int j = 0; j < 2; ++j) {
+            act[j] = e.on && z0 + j <= hi && m2_test(e.mz, z0 + j);
+            pw[j] = act[j] ? SF_AT(d.z_pos, z0 + j) : 0u;
+            cell[j] = (int)(pw[j] & POS_CELL);
         }
-        bool wander = false;
-        if (act) {
-            bool adjacent = false;
+        SF_UNROLL
+        for (int j = 0; j < 2; ++j) {
             SF_UNROLL
-            for (int i1 = 0; i1 < 4; ++i1) {
-                int nc = cell + sf_delta(i1);
-                uint32_t gn = SF_G(nc);
-                if (gn & C_S0) {
-                    adjacent = true;
-                    if (!(gn & C_S2) && e.on) {
-                        int b = sf_alloc_bullet(k, e);
-                        if (b >= 0) {
-                            int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
-                            sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+            for (int c = 0; c < 5; ++c) gv[j][c] = 0u;
+            if (act[j]) {
+                gv[j][0] = SF_G(cell[j]);
+                SF_UNROLL
+                for (int i1 = 0; i1 < 4; ++i1) gv[j][1 + i1] = SF_G(cell[j] + sf_delta(i1));
+            }
+        }
+        SF_UNROLL
+        for (int j = 0; j < 2; ++j) {
+            const int z = z0 + j;
+            bool go = act[j] && e.on && !(gv[j][0] & C_S2);
+            bool wander = false;
+            if (go) {
+                bool adjacent = false;
+                SF_UNROLL
+                for (int i1 = 0; i1 < 4; ++i1) {
+                    uint32_t gn = gv[j][1 + i1];
+                    if (gn & C_S0) {
+                        adjacent = true;
+                        if (!(gn & C_S2) && e.on) {
+                            int b = sf_alloc_bullet(k, e);
+                            if (b >= 0) {
+                                int nc = cell[j] + sf_delta(i1);
+                                int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
+                                sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+                                if (j == 0) { /* forward the new s[2] to the second zombie's copy */
+                                    if (cell[1] == nc) gv[1][0] = gn | C_S2;
+                                    SF_UNROLL
+                                    for (int c = 0; c < 4; ++c)
+                                        if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = gn | C_S2;
+                                }
+                            }
                         }
                     }
                 }
+                wander = !adjacent && e.on;
             }
-            wander = !adjacent && e.on;
-        }
-        if (wander) wander = !(sf_rand(e, t) % 5 < 2);
-        for (int i1 = 0; i1 < 2; ++i1) {
-            if (wander) {
-                int i2 = sf_rand(e, t) % 4;
-                int nc = cell + sf_delta(i2);
-                uint32_t gn = SF_G(nc);
-                if (sf_showit(t.smap[nc], gn) == SH_DOT) {
-                    SF_G(nc) = (uint16_t)(C_S1 | (uint32_t)z);
-                    SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
-                    SF_AT(d.z_pos, z) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
-                    wander = false;
+            if (wander) wander = !(sf_rand(e, t) % 5 < 2);
+            for (int i1 = 0; i1 < 2; ++i1) {
+                if (wander) {
+                    int i2 = sf_rand(e, t) % 4;
+                    int nc = cell[j] + sf_delta(i2);
+                    uint32_t gn = i2 == 0 ? gv[j][1] : i2 == 1 ? gv[j][2] : i2 == 2 ? gv[j][3] : gv[j][4];
+                    if (sf_showit(t.smap[nc], gn) == SH_DOT) {
+                        uint32_t vnew = C_S1 | (uint32_t)z, vold = gv[j][0] & ~(C_S1 | C_OCC);
+                        SF_G(nc) = (uint16_t)vnew;
+                        SF_G(cell[j]) = (uint16_t)vold;
+                        SF_AT(d.z_pos, z) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc);
+                        if (j == 0) {
+                            if (cell[1] == nc) gv[1][0] = vnew;
+                            SF_UNROLL
+                            for (int c = 0; c < 4; ++c) {
+                                if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = vnew;
+                                if (cell[1] + sf_delta(c) == cell[0]) gv[1][1 + c] = vold;
+                            }
+                        }
+                        wander = false;
+                    }
                 }
             }
         }
@@ -442,17 +476,28 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
     }
 }
 
-/* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates */
+/* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates.  Four exits
+ * per round so that their cells load together; exits are distinct cells, so the rounds need no
+ * forwarding. */
 SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mp) : -1);
-    for (int i = 0; i <= hi; ++i) {
-        if (e.on && m2_test(e.mp, i)) {
-            int cell = sf_exit_cell(d, k, env, i);
-            uint32_t g = SF_G(cell);
-            if (g & (C_S0 | C_S1 | C_S2)) {
+    for (int i0 = 0; i0 <= hi; i0 += 4) {
+        bool lv[4];
+        int cell[4];
+        uint32_t g[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            lv[j] = e.on && i0 + j <= hi && m2_test(e.mp, i0 + j);
+            cell[j] = lv[j] ? sf_exit_cell(d, k, env, i0 + j) : 0;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if (lv[j] && e.on && (g[j] & (C_S0 | C_S1 | C_S2))) {
                 int b = sf_alloc_bullet(k, e);
-                if (b >= 0) sf_place_bullet(d, env, e, b, cell, g, 2, 1, -1, 20, -10);
+                if (b >= 0) sf_place_bullet(d, env, e, b, cell[j], g[j], 2, 1, -1, 20, -10);
             }
         }
         SF_SYNCWARP();
@@ -483,24 +528,35 @@ SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, i
     }
 }
 
-/* update_tmp, gameplay.hpp:1343-1381 */
+/* update_tmp, gameplay.hpp:1343-1381.  Four bullets per round (positions, then cells, loaded
+ * together); whether a bullet is absorbed depends on the cell's kind and occupant only, which
+ * no absorption changes, so the rounds need no forwarding. */
 SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
     const bool any = e.on && e.ntemp != 0; /* nothing player-built: no bullet can be absorbed */
     const int hi = SF_WARP_MAX(any ? m2_highest(e.mb) : -1);
     int hit_cell[4];
     int n_hit = 0;
-    for (int b = 0; b <= hi; ++b) {
-        if (any && m2_test(e.mb, b)) {
-            int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
-            uint32_t g = SF_G(cell);
-            uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-            if (kind == K_BLOCK || (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)))) {
-                int q = sf_find_built(d, env, e, cell);
-                SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b);
-                SF_G(cell) = (uint16_t)(g & ~C_S2);
-                m2_clear(e.mb, b);
-                if (n_hit < 4) hit_cell[n_hit] = cell;
+    for (int b0 = 0; b0 <= hi; b0 += 4) {
+        bool lv[4];
+        int cell[4];
+        uint32_t g[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            lv[j] = any && b0 + j <= hi && m2_test(e.mb, b0 + j);
+            cell[j] = lv[j] ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            uint32_t kind = (g[j] >> C_KIND_SHIFT) & 7u;
+            if (lv[j] && (kind == K_BLOCK || (kind == K_ENTRANCE && !(g[j] & (C_S0 | C_S1))))) {
+                int q = sf_find_built(d, env, e, cell[j]);
+                SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b0 + j);
+                SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
+                m2_clear(e.mb, b0 + j);
+                if (n_hit < 4) hit_cell[n_hit] = cell[j];
                 n_hit += 1;
             }
         }
@@ -600,18 +656,30 @@ SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
         }
         SF_SYNCWARP();
     }
+    /* four bullets per round: flags and positions, then the cells of the owners, load together;
+     * owners stand on distinct cells, so the rounds need no forwarding */
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
-    for (int b = 0; b <= hi; ++b) {
-        if (e.on && m2_test(e.mb, b)) {
-            uint32_t meta = SF_AT(d.b_meta, b);
-            if (meta & BF_OWNS) {
-                int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL);
-                uint32_t g = SF_G(cell);
-                if (g & C_S0) {
-                    int h = (int)(g & C_OCC);
-                    if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b, cell, g, meta);
-                } else if (g & C_S1) {
-                    sf_zombie_damage(d, env, e, (int)(g & C_OCC), b, cell, g, meta);
+    for (int b0 = 0; b0 <= hi; b0 += 4) {
+        bool own[4];
+        uint32_t meta[4], g[4];
+        int cell[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            bool lv = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
+            meta[j] = lv ? SF_AT(d.b_meta, b0 + j) : 0u;
+            cell[j] = lv ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
+            own[j] = lv && (meta[j] & BF_OWNS);
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) g[j] = own[j] ? (uint32_t)SF_G(cell[j]) : 0u;
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if (own[j]) {
+                if (g[j] & C_S0) {
+                    int h = (int)(g[j] & C_OCC);
+                    if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b0 + j, cell[j], g[j], meta[j]);
+                } else if (g[j] & C_S1) {
+                    sf_zombie_damage(d, env, e, (int)(g[j] & C_OCC), b0 + j, cell[j], g[j], meta[j]);
                 }
             }
         }
@@ -622,57 +690,81 @@ SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
 /* update_bull, gameplay.hpp:1059-1100, plus the harness's out-of-bounds guard.  Pass 1 is the
  * themap1 snapshot with s[2] cleared on the current and next cell of every live bullet; pass 2
  * walks the bullets in the REVERSE of the reference's order so that the first bullet to reach
- * a cell here is the reference's last writer of it. */
+ * a cell here is the reference's last writer of it.  Both passes take four bullets per round:
+ * positions, then cells, load together; pass 2 forwards a newly set s[2] to the later bullets
+ * of its round. */
 SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
     bool oob = false;
-    for (int b = 0; b <= hi; ++b) {
-        if (e.on && m2_test(e.mb, b)) {
-            uint32_t pw = SF_AT(d.b_pw, b);
-            int nc;
-            if (!sf_neighbour((int)(pw & POS_CELL), (int)(pw >> POS_HI_SHIFT), &nc)) oob = true;
+    for (int b0 = 0; b0 <= hi; b0 += 4) {
+        bool lv[4];
+        int cell[4], nc[4];
+        uint32_t g[4], gn[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            lv[j] = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
+            uint32_t pw = lv[j] ? SF_AT(d.b_pw, b0 + j) : 0u;
+            cell[j] = (int)(pw & POS_CELL);
+            if (lv[j] && !sf_neighbour(cell[j], (int)(pw >> POS_HI_SHIFT), &nc[j])) {
+                oob = true; /* the reference would read themap[i][-1][k], :1069 */
+                lv[j] = false;
+            }
         }
-    }
-    if (oob) sf_fail_env(e, SF_UB_GUARD); /* the reference would read themap[i][-1][k], :1069 */
-    SF_SYNCWARP();
-    for (int b = 0; b <= hi; ++b) {
-        if (e.on && m2_test(e.mb, b)) {
-            uint32_t pw = SF_AT(d.b_pw, b);
-            int cell = (int)(pw & POS_CELL);
-            int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
-            uint32_t g = SF_G(cell);
-            if (g & C_S2) SF_G(cell) = (uint16_t)(g & ~C_S2);
-            uint32_t gn = SF_G(nc);
-            if (gn & C_S2) SF_G(nc) = (uint16_t)(gn & ~C_S2);
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
+            gn[j] = lv[j] ? (uint32_t)SF_G(nc[j]) : 0u;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if (g[j] & C_S2) SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
+            if (gn[j] & C_S2) SF_G(nc[j]) = (uint16_t)(gn[j] & ~C_S2);
         }
         SF_SYNCWARP();
     }
+    if (oob) sf_fail_env(e, SF_UB_GUARD);
     int r = 0;
     if (e.on) r = sf_rand(e, t) & 1;
     SF_SYNCWARP();
     /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
-    for (int i = 0; i <= hi; ++i) {
-        int b = r ? hi - i : i;
-        if (e.on && m2_test(e.mb, b)) {
-            uint32_t pw = SF_AT(d.b_pw, b);
-            uint32_t meta = SF_AT(d.b_meta, b) & ~BF_OWNS;
-            int cell = (int)(pw & POS_CELL);
-            uint32_t range = meta & 0xFFu, trav = (meta >> 8) & 0xFFu;
-            if (trav + 1 >= range) { /* Bullet::expire, Item.hpp:165-168 */
-                m2_clear(e.mb, b);
-            } else {
-                int nc = cell + sf_delta((int)(pw >> POS_HI_SHIFT));
-                uint32_t gn = SF_G(nc);
-                int sit = sf_showit(t.smap[nc], gn);
-                bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
+    for (int i0 = 0; i0 <= hi; i0 += 4) {
+        bool lv[4];
+        int b[4], nc[4];
+        uint32_t pw[4], meta[4], gn[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            b[j] = r ? hi - (i0 + j) : i0 + j;
+            lv[j] = e.on && i0 + j <= hi && m2_test(e.mb, b[j]);
+            pw[j] = lv[j] ? SF_AT(d.b_pw, b[j]) : 0u;
+            meta[j] = lv[j] ? (SF_AT(d.b_meta, b[j]) & ~BF_OWNS) : 0u;
+            nc[j] = (int)(pw[j] & POS_CELL) + sf_delta((int)(pw[j] >> POS_HI_SHIFT));
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            bool expired = ((meta[j] >> 8) & 0xFFu) + 1 >= (meta[j] & 0xFFu); /* Bullet::expire, Item.hpp:165-168 */
+            if (lv[j] && expired) {
+                m2_clear(e.mb, b[j]);
+                lv[j] = false;
+            }
+            gn[j] = lv[j] ? (uint32_t)SF_G(nc[j]) : 0u;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if (lv[j]) {
+                int sit = sf_showit(t.smap[nc[j]], gn[j]);
+                bool built = ((gn[j] >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
                 if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
-                    if (!(gn & C_S2)) meta |= BF_OWNS;
-                    SF_G(nc) = (uint16_t)(gn | C_S2);
-                    SF_AT(d.b_pw, b) = (uint16_t)((pw & ~POS_CELL) | (uint32_t)nc);
-                    SF_AT(d.b_meta, b) = meta + 0x100u;
+                    uint32_t m = meta[j];
+                    if (!(gn[j] & C_S2)) m |= BF_OWNS;
+                    SF_G(nc[j]) = (uint16_t)(gn[j] | C_S2);
+                    SF_AT(d.b_pw, b[j]) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc[j]);
+                    SF_AT(d.b_meta, b[j]) = m + 0x100u;
+                    SF_UNROLL
+                    for (int jj = j + 1; jj < 4; ++jj)
+                        if (nc[jj] == nc[j]) gn[jj] |= C_S2;
                 } else {
-                    m2_clear(e.mb, b);
+                    m2_clear(e.mb, b[j]);
                 }
             }
         }

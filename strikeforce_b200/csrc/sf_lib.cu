@@ -22,7 +22,9 @@
 #include "sf_host_setup.h"
 #include "sf_obs.cuh"
 
-#define SF_CTA 512
+#ifndef SF_CTA
+#define SF_CTA 1024 /* threads per CTA = arenas in flight per SM (one CTA per SM) */
+#endif
 #define SF_SMEM_EXP 131072
 #define SF_SMEM_MAP 9008
 #define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP)
@@ -321,9 +323,9 @@ void carve(Carver &c, sf_handle &h)
     c.take(d.grid, E * SF_GRID_STRIDE);
     c.take(d.out, E);
     c.take(d.stats, (size_t)SF_STAT_COUNT);
-    uint8_t *smap;
-    uint16_t *exp_tab, *log_tab;
-    float *lut;
+    uint8_t *smap = nullptr;
+    uint16_t *exp_tab = nullptr, *log_tab = nullptr;
+    float *lut = nullptr;
     c.take(smap, (size_t)SF_SMEM_MAP), c.take(exp_tab, (size_t)65536), c.take(log_tab, (size_t)65536);
     c.take(lut, (size_t)SF_POW_LUT_LEN);
     d.smap = smap, d.exp_tab = exp_tab, d.log_tab = log_tab, d.pow_lut = lut, d.pow_lut_len = SF_POW_LUT_LEN;

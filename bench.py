@@ -230,17 +230,14 @@ def run_ours(args):
         sampler.stop_flag.set()
         sampler.join()
     # ---- reduce over ranks: max time, summed statistics (the only collective: NCCL all-reduce)
-    tm = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=sim.device)
-    d_dev, d_e2e = (st1 - st0), (st3 - st2)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(d_dev, op=dist.ReduceOp.SUM)
-        dist.all_reduce(d_e2e, op=dist.ReduceOp.SUM)
-    ms_dev, ms_e2e = tm.cpu().tolist()
+    local_algo = float((st1 - st0)[sfcfg.STAT_NAMES.index("algo_bytes")].item())
+    from strikeforce_b200 import dist as sfdist
+    ms_dev = sfdist.max_over_ranks(ms_dev, sim.device)
+    ms_e2e = sfdist.max_over_ranks(ms_e2e, sim.device)
+    d_dev, d_e2e = sfdist.reduce_stats(st1 - st0), sfdist.reduce_stats(st3 - st2)
     names = sfcfg.STAT_NAMES
     d_dev = dict(zip(names, d_dev.cpu().tolist()))
     d_e2e = dict(zip(names, d_e2e.cpu().tolist()))
-    local_algo = float((st1 - st0)[names.index("algo_bytes")].item())
     if rank == 0:
         peak, peak_src = load_peaks()
         steps_done = d_dev["steps"] + d_dev["overflows"] + d_dev["ub_guards"]

@@ -45,7 +45,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
     f[0] = k.mode, f[1] = e.level, f[2] = (int32_t)e.frame, f[3] = e.kills, f[4] = e.tkills, f[5] = e.loot;
     f[6] = e.chest, f[7] = 0;
     sink.elem(SF_K_HEADER, 0, f, SF_NF_HEADER);
-    for (int i = 0; i < 18; ++i) f[i] = e.L[i] == SF_RNG_ZERO ? 0 : (int32_t)t.exp_tab[e.L[i]] + 1;
+    for (int i = 0; i < 18; ++i) f[i] = (int32_t)t.exp_tab[sf_rng_log(e, i)] + 1;
     f[18] = (int32_t)(e.jomle & 0xFFFFu);
     sink.elem(SF_K_RNG, 0, f, SF_NF_RNG);
     for (int h = 0; h < e.hw_h; ++h) {

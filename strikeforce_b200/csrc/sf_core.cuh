@@ -46,6 +46,8 @@ struct SfTabs {
     const uint8_t *smap;     /* static map bytes [SF_CELLS] */
     const uint16_t *exp_tab; /* [65536] */
     const uint16_t *log_tab; /* [65536] */
+    const uint32_t *rng_cst; /* [2][18][E] per-arena term constants (terms 10..17 are read on demand) */
+    int32_t E;
 };
 
 /* register-resident part of one arena while a kernel works on it */
@@ -56,9 +58,12 @@ struct SfEnv {
     uint64_t mh, mz[2], mb[2], mp[2];
     uint64_t quit;       /* humans whose Hp was zeroed by '_' (gameplay.hpp:696-699) */
     bool on;             /* this lane holds an arena that is still running this step */
-    uint32_t L[18];      /* log_3 of random[0..17] (random.hpp:31) */
-    uint32_t cst[18];    /* 2*seed[i] | 2*log_3(us[i]) << 8 */
-    uint32_t draws;      /* _rand() calls in this kernel (statistics) */
+    int env;             /* arena index of this lane */
+    uint32_t Lp[9];      /* log_3 of random[0..17] (random.hpp:31), two 16-bit logs per word */
+    uint32_t cst[10];    /* terms 0..9: 2*seed[i] | 2*log_3(us[i]) << 8 */
+    uint32_t W;          /* sum of the values random[10..17] (see sf_rand) */
+    bool fast;           /* both seeds below 10^10: terms 10..17 are the plain window W */
+    bool bank;           /* which half of rng_cst holds this stream's term constants */
 };
 
 /* ------------------------------------------------------------------ small helpers */
@@ -174,51 +179,145 @@ SF_FN int sf_showit(uint32_t st, uint32_t g)
 /* ------------------------------------------------------------------ random.hpp */
 
 /* _rand(), random.hpp:54-62, in the discrete-log domain of the cyclic group mod 65537
- * (generator 3).  random[i]^seed[i] * us[i] = 3^(L[i]*seed[i] + log us[i]); the new element
- * (sum)^jomle = 3^(log(sum) * jomle).  exp_tab holds 3^k - 1, so the reference's
- * "1 + sum of 18 terms" is 19 + sum of 18 table entries.  WARM handles the all-zero start of
- * _srand (:64-76), where 0^seed = 0 contributes nothing. */
-template <bool WARM>
-SF_FN int sf_rand_t(SfEnv &e, const SfTabs &t)
+ * (generator 3): random[i]^seed[i] * us[i] = 3^(L[i]*seed[i] + log us[i]) and the new element
+ * (sum)^jomle = 3^(log(sum) * jomle).  exp_tab holds 3^k - 1, so a term is "entry + 1".
+ *
+ * Seeds below 10^10 (a unix time, a 30-bit serial: gameplay.hpp:1745-1747) have digits 10..17
+ * equal to 0, i.e. seed[i] = us[i] = 1 there, so those eight terms are the plain values
+ * random[10..17] -- a window that slides by one element per draw.  Arenas flagged `fast` keep
+ * that window sum in W (minus the element leaving, plus the new one) and look up only the ten
+ * leading terms; a lane with longer seeds takes the eight extra look-ups itself. */
+SF_FN uint32_t sf_rng_log(const SfEnv &e, int i) { return (e.Lp[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; }
+
+SF_FN uint32_t sf_rng_term(const SfTabs &t, uint32_t L, uint32_t c)
 {
-    uint32_t S = WARM ? 1u : 19u;
-    const uint8_t *ebytes = (const uint8_t *)t.exp_tab;
-SF_UNROLL
-    for (int i = 0; i < 18; ++i) {
-        uint32_t c = e.cst[i];
-        uint32_t off = (e.L[i] * (c & 0xFFu) + (c >> 8)) & 0x1FFFEu;
-        uint32_t v = *(const uint16_t *)(ebytes + off);
-        if (WARM) S += (e.L[i] == SF_RNG_ZERO) ? 0u : v + 1u;
-        else S += v;
+    uint32_t off = (L * (c & 0xFFu) + (c >> 8)) & 0x1FFFEu;
+    return *(const uint16_t *)((const uint8_t *)t.exp_tab + off);
+}
+
+SF_FN int sf_rand(SfEnv &e, const SfTabs &t)
+{
+    uint32_t S = 11u; /* 1 + ten terms of "entry + 1" */
+    SF_UNROLL
+    for (int i = 0; i < 10; ++i) S += sf_rng_term(t, sf_rng_log(e, i), e.cst[i]);
+    if (e.fast) {
+        S += e.W;
+    } else { /* a plain per-lane branch: draws happen in divergent code, no warp vote here */
+        S += 8u;
+        SF_UNROLL
+        for (int i = 10; i < 18; ++i) S += sf_rng_term(t, sf_rng_log(e, i), t.rng_cst[((size_t)(e.bank ? 18 : 0) + (size_t)i) * (size_t)t.E + (size_t)e.env]);
     }
-    int32_t r = (int32_t)(S & 0xFFFFu) - (int32_t)(S >> 16); /* 65536 == -1 (mod 65537) */
+    /* S < 2^21: fold with 65536 == -1 (mod 65537) */
+    int32_t r = (int32_t)(S & 0xFFFFu) - (int32_t)(S >> 16);
     if (r < 0) r += 65537;
     if (r == 0) r = 1;                                        /* sum + (sum == 0) */
     uint32_t lg = t.log_tab[r - 1];
     e.jomle += 1;
     uint32_t ln = (lg * (e.jomle & 0xFFFFu)) & 0xFFFFu;       /* binpow(sum, jomle), :42-52 */
-SF_UNROLL
-    for (int i = 0; i < 17; ++i) e.L[i] = e.L[i + 1];
-    e.L[17] = ln;
-    e.draws += 1;
-    return (int)(((uint32_t)t.exp_tab[ln] + 1u) & 1023u);
+    uint32_t val = (uint32_t)t.exp_tab[ln] + 1u;
+    e.W += val - ((uint32_t)t.exp_tab[sf_rng_log(e, 10)] + 1u); /* element 10 leaves the window */
+    SF_UNROLL
+    for (int j = 0; j < 8; ++j) e.Lp[j] = (e.Lp[j] >> 16) | (e.Lp[j + 1] << 16);
+    e.Lp[8] = (e.Lp[8] >> 16) | (ln << 16);
+    return (int)(val & 1023u);
 }
-SF_FN int sf_rand(SfEnv &e, const SfTabs &t) { return sf_rand_t<false>(e, t); }
 
-/* _srand(tb, u_s), random.hpp:64-76 */
-SF_FN void sf_srand(SfEnv &e, const SfTabs &t, int64_t tb, int64_t u_s)
+/* ---- _srand(tb, u_s), random.hpp:64-76 -------------------------------------------------
+ * Seeding digit-splits both seeds, starts from eighteen zeros and discards 1024 draws.  The
+ * draws are strictly serial (about 0.2 ms of dependent work), far longer than a whole step of
+ * the batch, so an episode's stream is never warmed up on the step path: every arena carries
+ * a PENDING stream -- the one its next episode will use -- which each step advances by
+ * SF_WARM_PER_STEP draws with all lanes in lock step.  When the episode ends the pending stream
+ * is installed (any draws still missing are made then) and the stream after it is seeded.
+ *
+ * During the warm-up zero has no logarithm; but after n draws the zeros are exactly the
+ * elements 0 .. 17-n, so term i simply counts only when i + n >= 18. */
+#define SF_WARM_DRAWS 1024u
+#define SF_WARM_PER_STEP 8
+
+SF_FN size_t sf_cst_index(const SfDev &d, int bank, int i, int env)
 {
-SF_UNROLL
+    return ((size_t)bank * 18 + (size_t)i) * (size_t)d.E + (size_t)env;
+}
+
+/* one warm-up draw of a stream held as packed logs Lp[9] with term constants c[18];
+ * n = draws made so far (jomle = 18 + n) */
+SF_FN void sf_warm_draw(const SfTabs &t, uint32_t Lp[9], const uint32_t c[18], uint32_t n)
+{
+    uint32_t S = 1u;
+    SF_UNROLL
+    for (int i = 0; i < 18; ++i) {
+        uint32_t L = (Lp[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        uint32_t term = sf_rng_term(t, L, c[i]) + 1u;
+        if ((uint32_t)i + n >= 18u) S += term;
+    }
+    int32_t r = (int32_t)(S & 0xFFFFu) - (int32_t)(S >> 16);
+    if (r < 0) r += 65537;
+    if (r == 0) r = 1;
+    uint32_t jomle = 18u + n + 1u;
+    uint32_t ln = ((uint32_t)t.log_tab[r - 1] * (jomle & 0xFFFFu)) & 0xFFFFu;
+    SF_UNROLL
+    for (int j = 0; j < 8; ++j) Lp[j] = (Lp[j] >> 16) | (Lp[j + 1] << 16);
+    Lp[8] = (Lp[8] >> 16) | (ln << 16);
+}
+
+/* digit-split the seeds of a stream into term constants of `bank` and mark it un-warmed */
+SF_FN void sf_seed_pending(const SfDev &d, const SfTabs &t, int env, int bank, int64_t tb, int64_t u_s)
+{
+    uint32_t fast = (tb < 10000000000ll && u_s < 10000000000ll) ? 1u : 0u;
     for (int i = 0; i < 18; ++i) {
         uint32_t us = (uint32_t)(u_s % 10 + 1), sd = (uint32_t)(tb % 10 + 1);
         u_s /= 10;
         tb /= 10;
-        e.cst[i] = (2u * sd) | ((2u * (uint32_t)t.log_tab[us - 1]) << 8);
-        e.L[i] = SF_RNG_ZERO;
+        d.rng_cst[sf_cst_index(d, bank, i, env)] = (2u * sd) | ((2u * (uint32_t)t.log_tab[us - 1]) << 8);
     }
-    e.jomle = 18;
-    for (int i = 0; i < 18; ++i) sf_rand_t<true>(e, t);
-    for (int i = 18; i < 1024; ++i) sf_rand_t<false>(e, t);
+    SF_UNROLL
+    for (int j = 0; j < 9; ++j) SF_AT(d.pend_log, j) = 0u;
+    d.pend_n[env] = fast << 16;
+}
+
+/* advance the pending stream of arena `env` by up to `budget` draws */
+SF_FN void sf_advance_pending(const SfDev &d, const SfTabs &t, int env, bool valid, int budget)
+{
+    uint32_t pn = valid ? d.pend_n[env] : SF_WARM_DRAWS;
+    uint32_t n = pn & 0xFFFFu;
+    if (n < SF_WARM_DRAWS) {
+        const int bank = (int)((d.misc[env] >> 25) & 1u) ^ 1;
+        uint32_t Lp[9], c[18];
+        SF_UNROLL
+        for (int j = 0; j < 9; ++j) Lp[j] = SF_AT(d.pend_log, j);
+        SF_UNROLL
+        for (int i = 0; i < 18; ++i) c[i] = d.rng_cst[sf_cst_index(d, bank, i, env)];
+        for (int j = 0; j < budget; ++j) {
+            if (n < SF_WARM_DRAWS) {
+                sf_warm_draw(t, Lp, c, n);
+                n += 1;
+            }
+        }
+        SF_UNROLL
+        for (int j = 0; j < 9; ++j) SF_AT(d.pend_log, j) = Lp[j];
+        d.pend_n[env] = (pn & ~0xFFFFu) | n;
+    }
+    /* no warp barrier here: sf_install_stream calls this from a single lane */
+}
+
+/* make the pending stream the arena's stream (finishing its warm-up if need be) and seed the
+ * stream of the episode after it */
+SF_FN void sf_install_stream(const SfDev &d, const SfTabs &t, int env, SfEnv &e, int64_t next_tb, int64_t next_serial)
+{
+    sf_advance_pending(d, t, env, true, (int)SF_WARM_DRAWS);
+    e.bank = !e.bank;
+    e.fast = (d.pend_n[env] >> 16) & 1u;
+    SF_UNROLL
+    for (int j = 0; j < 9; ++j) e.Lp[j] = SF_AT(d.pend_log, j);
+    SF_UNROLL
+    for (int i = 0; i < 10; ++i) e.cst[i] = d.rng_cst[sf_cst_index(d, e.bank ? 1 : 0, i, env)];
+    e.jomle = 18u + SF_WARM_DRAWS;
+    e.W = 0;
+    for (int i = 10; i < 18; ++i) e.W += (uint32_t)t.exp_tab[sf_rng_log(e, i)] + 1u;
+    /* the header must carry the new bank before the next pending stream is addressed */
+    d.misc[env] = (d.misc[env] & ~(1u << 25)) | (e.bank ? 1u << 25 : 0u);
+    sf_seed_pending(d, t, env, e.bank ? 0 : 1, next_tb, next_serial);
 }
 
 /* ------------------------------------------------------------------ entities */
@@ -535,7 +634,7 @@ SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
     const bool any = e.on && e.ntemp != 0; /* nothing player-built: no bullet can be absorbed */
     const int hi = SF_WARP_MAX(any ? m2_highest(e.mb) : -1);
-    int hit_cell[4];
+    int hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0; /* cells that absorbed a bullet in this call */
     int n_hit = 0;
     for (int b0 = 0; b0 <= hi; b0 += 4) {
         bool lv[4];
@@ -556,7 +655,10 @@ SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
                 SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b0 + j);
                 SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
                 m2_clear(e.mb, b0 + j);
-                if (n_hit < 4) hit_cell[n_hit] = cell[j];
+                if (n_hit == 0) hc0 = cell[j];
+                else if (n_hit == 1) hc1 = cell[j];
+                else if (n_hit == 2) hc2 = cell[j];
+                else if (n_hit == 3) hc3 = cell[j];
                 n_hit += 1;
             }
         }
@@ -568,8 +670,10 @@ SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
         for (int q = (int)e.ntemp - 1; q >= 0; --q)
             if (q < (int)e.ntemp) sf_check_built(d, k, env, e, SF_T(d.t_cell, q));
     } else {
-        for (int i = 0; i < 4; ++i)
-            if (i < n_hit) sf_check_built(d, k, env, e, hit_cell[i]);
+        if (n_hit > 0) sf_check_built(d, k, env, e, hc0);
+        if (n_hit > 1) sf_check_built(d, k, env, e, hc1);
+        if (n_hit > 2) sf_check_built(d, k, env, e, hc2);
+        if (n_hit > 3) sf_check_built(d, k, env, e, hc3);
     }
     SF_SYNCWARP();
 }
@@ -779,18 +883,15 @@ SF_FN int sf_rnpc_bot(const SfTabs &t, SfEnv &e, bool want)
     int c = '+';
     bool pick_weapon = want && (e.frame % 50 <= 1);
     bool more = want && !pick_weapon;
-    if (pick_weapon) {
-        const char w[8] = {'c', 'v', 'b', 'n', 'm', ',', '.', '/'};
-        c = w[sf_rand(e, t) % 8];
-    }
+    /* the key rows of the reference are packed eight symbols to a 64-bit constant */
+    if (pick_weapon) c = (int)((0x2f2e2c6d6e627663ull >> (8 * (sf_rand(e, t) % 8))) & 0xFFu); /* "cvbnm,./" */
     if (more && sf_rand(e, t) % 5 < 3) c = 'x', more = false;
     bool second = false;
     if (more) second = sf_rand(e, t) % 5 < 3;
     if (more) {
         int r = sf_rand(e, t);
-        const char a[7] = {'1', '2', 'a', 'w', 's', 'd', 'p'};
-        const char o[8] = {'+', 'u', 'f', 'g', 'h', 'j', '[', ']'};
-        c = second ? a[r % 7] : o[r % 8];
+        c = second ? (int)((0x0070647377613231ull >> (8 * (r % 7))) & 0xFFu)  /* "12awsdp" */
+                   : (int)((0x5d5b6a686766752bull >> (8 * (r % 8))) & 0xFFu); /* "+ufghj[]" */
     }
     return c;
 }
@@ -984,10 +1085,13 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
 SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e,
                            const uint8_t *actions)
 {
-    uint8_t cmd[SF_LIM_HUMANS];
+    /* commands wait in h_cmd between the two loops (command[], gameplay.hpp:43) */
     const uint64_t live = e.on ? e.mh : 0ull;
     const int hi = SF_WARP_MAX(live ? sf_fls64(live) : -1);
-    cmd[0] = (actions && e.on) ? actions[0] : (uint8_t)'+';
+    const int cmd0 = (actions && e.on) ? actions[0] : '+';
+#ifdef SF_EXP_CMDLOCAL
+    uint8_t cmdl[SF_LIM_HUMANS];
+#endif
     for (int h = 1; h <= hi; ++h) {
         bool is_live = (live >> h) & 1;
         uint32_t sel = is_live ? SF_AT(d.h_sel, h) : 0u;
@@ -1001,7 +1105,11 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
                 if (!ok) c = '+';
             }
         }
-        cmd[h] = (uint8_t)c;
+#ifdef SF_EXP_CMDLOCAL
+        cmdl[h] = (uint8_t)c;
+#else
+        if (is_live) SF_AT(d.h_cmd, h) = (uint8_t)c;
+#endif
         SF_SYNCWARP();
     }
     int r = 0;
@@ -1009,7 +1117,11 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     SF_SYNCWARP();
     for (int i = 0; i <= hi; ++i) {
         int h = r ? i : hi - i;
-        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, cmd[h]);
+#ifdef SF_EXP_CMDLOCAL
+        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, h == 0 ? cmd0 : (int)cmdl[h]);
+#else
+        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h));
+#endif
         SF_SYNCWARP();
     }
 }
@@ -1030,8 +1142,7 @@ SF_FN void sf_clear_grid(uint16_t *g)
 
 /* setup() + load_data() + _srand, gameplay.hpp:1231-1277, 1741-1747, 1861-1920; the harness
  * then does "++frame" (play(), :1441) */
-SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int64_t tb,
-                        int64_t serial)
+SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
     sf_clear_grid(d.grid + (size_t)env * SF_GRID_STRIDE);
     int64_t ge = k.env_id_base + env;
@@ -1064,7 +1175,8 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         e.mh = 1ull;
         e.hw_h = 1;
     }
-    sf_srand(e, t, tb, serial);
+    /* the stream of this episode was seeded as the pending one; the next episode's follows */
+    sf_install_stream(d, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode + 1));
 }
 
 /* ------------------------------------------------------------------ the step */
@@ -1134,31 +1246,32 @@ SF_FN void sf_load_env(const SfDev &d, int env, SfEnv &e)
     e.mb[0] = SF_AT(d.mb, 0), e.mb[1] = SF_AT(d.mb, 1);
     e.mp[0] = SF_AT(d.mp, 0), e.mp[1] = SF_AT(d.mp, 1);
     e.quit = 0;
+    e.env = env;
+    e.fast = (misc >> 24) & 1u;
+    e.bank = (misc >> 25) & 1u;
     SF_UNROLL
-    for (int i = 0; i < 18; ++i) {
-        e.L[i] = SF_AT(d.rng_log, i);
-        e.cst[i] = SF_AT(d.rng_cst, i);
-    }
+    for (int j = 0; j < 9; ++j) e.Lp[j] = SF_AT(d.rng_log, j);
+    SF_UNROLL
+    for (int i = 0; i < 10; ++i) e.cst[i] = d.rng_cst[sf_cst_index(d, e.bank ? 1 : 0, i, env)];
+    e.W = d.rng_w[env];
     e.jomle = d.jomle[env];
-    e.draws = 0;
     e.on = e.status == SF_RUNNING;
 }
 
-SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e, bool store_cst)
+SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e)
 {
     d.frame[env] = e.frame;
     d.kills[env] = e.kills, d.tkills[env] = e.tkills, d.loot[env] = e.loot, d.chest[env] = e.chest;
-    d.misc[env] = (uint32_t)e.level | ((uint32_t)e.status << 8) | ((uint32_t)e.hw_h << 16);
+    d.misc[env] = (uint32_t)e.level | ((uint32_t)e.status << 8) | ((uint32_t)e.hw_h << 16) | (e.fast ? 1u << 24 : 0u) |
+                  (e.bank ? 1u << 25 : 0u);
     d.steps[env] = e.steps, d.episode[env] = e.episode, d.ntemp[env] = e.ntemp;
     d.mh[env] = e.mh;
     SF_AT(d.mz, 0) = e.mz[0], SF_AT(d.mz, 1) = e.mz[1];
     SF_AT(d.mb, 0) = e.mb[0], SF_AT(d.mb, 1) = e.mb[1];
     SF_AT(d.mp, 0) = e.mp[0], SF_AT(d.mp, 1) = e.mp[1];
     SF_UNROLL
-    for (int i = 0; i < 18; ++i) {
-        SF_AT(d.rng_log, i) = (uint16_t)e.L[i];
-        if (store_cst) SF_AT(d.rng_cst, i) = e.cst[i];
-    }
+    for (int j = 0; j < 9; ++j) SF_AT(d.rng_log, j) = e.Lp[j];
+    d.rng_w[env] = e.W;
     d.jomle[env] = e.jomle;
 }
 
@@ -1188,9 +1301,11 @@ SF_FN void sf_reset_body(const SfDev &d, const SfConst &k, const SfTabs &t, int 
 {
     SfEnv e;
     e.episode = episode;
-    e.draws = 0;
-    sf_reset_env(d, k, t, env, e, tb, serial);
-    sf_store_env(d, env, e, true);
+    e.env = env;
+    e.bank = (d.misc[env] >> 25) & 1u;
+    sf_seed_pending(d, t, env, e.bank ? 0 : 1, tb, serial);
+    sf_reset_env(d, k, t, env, e);
+    sf_store_env(d, env, e);
     sf_step_out o;
     o.status = SF_RUNNING, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0;
     o.episode_steps = 0;
@@ -1200,19 +1315,30 @@ SF_FN void sf_reset_body(const SfDev &d, const SfConst &k, const SfTabs &t, int 
 /* one env-step (or one half of it) for arena `env`; `actions` is the arena's row of the
  * action buffer (NULL for SF_HALF_A).  `valid` is false for the padding lanes of the last
  * warp: they walk through the same code with nothing to do, so that every lane of a warp
- * reaches every SF_SYNCWARP(). */
+ * reaches every SF_SYNCWARP().
+ *
+ * Nothing but `e` stays in registers across the tick: the step output starts as "minus the
+ * values at entry" in d.out and gets the values at exit added, and the statistics read the
+ * entry values back from the header arrays, which are only overwritten by sf_store_env. */
 SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int env, bool valid,
                         const uint8_t *actions, int half, SfStatDelta &sd)
 {
+    if (half != SF_HALF_B) {
+        sf_advance_pending(d, t, env, valid, SF_WARM_PER_STEP);
+        SF_SYNCWARP();
+    }
     SfEnv e;
     sf_load_env(d, env, e);
     if (!valid) e.on = false;
     const bool was_on = e.on;
-    sf_step_out o;
-    if (half == SF_HALF_B) o = d.out[env];
-    else o.status = 0, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0, o.episode_steps = 0;
-    int32_t kills0 = e.kills, tkills0 = e.tkills, loot0 = e.loot;
-    int32_t hp0 = SF_AT(d.h_hp, 0), dmg0 = SF_AT(d.h_dmg, 0), eff0 = SF_AT(d.h_eff, 0);
+    if (valid) {
+        sf_step_out o;
+        if (half == SF_HALF_B) o = d.out[env];
+        else o.status = 0, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0, o.episode_steps = 0;
+        o.d_kills -= e.kills, o.d_teams_kills -= e.tkills, o.d_loot -= e.loot;
+        o.d_hp -= SF_AT(d.h_hp, 0), o.d_damage -= SF_AT(d.h_dmg, 0), o.d_effect -= SF_AT(d.h_eff, 0);
+        d.out[env] = o;
+    }
     if (half != SF_HALF_B) {
         if (e.on) sd.algo_bytes += sf_algo_bytes(k, e);
         sf_step_a(d, k, t, env, e);
@@ -1220,16 +1346,17 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
     if (half != SF_HALF_A) sf_step_b(d, k, t, env, e, actions);
     if (valid) {
         /* a terminal arena that is not auto-reset waits for sf_reset: report, change nothing */
-        o.d_kills += e.kills - kills0, o.d_teams_kills += e.tkills - tkills0, o.d_loot += e.loot - loot0;
-        o.d_hp += SF_AT(d.h_hp, 0) - hp0, o.d_damage += SF_AT(d.h_dmg, 0) - dmg0, o.d_effect += SF_AT(d.h_eff, 0) - eff0;
+        sf_step_out o = d.out[env];
+        o.d_kills += e.kills, o.d_teams_kills += e.tkills, o.d_loot += e.loot;
+        o.d_hp += SF_AT(d.h_hp, 0), o.d_damage += SF_AT(d.h_dmg, 0), o.d_effect += SF_AT(d.h_eff, 0);
         o.status = e.status;
         o.episode_steps = (int32_t)e.steps;
         d.out[env] = o;
     }
     bool reset = false;
     if (was_on) {
-        sd.kills += e.kills - kills0, sd.tkills += e.tkills - tkills0, sd.loot += e.loot - loot0;
-        sd.draws += e.draws;
+        sd.kills += e.kills - d.kills[env], sd.tkills += e.tkills - d.tkills[env], sd.loot += e.loot - d.loot[env];
+        sd.draws += e.jomle - d.jomle[env];
         if (half != SF_HALF_A && (e.status == SF_RUNNING || e.status == SF_WIN || e.status == SF_DEAD ||
                                   e.status == SF_TIMEOUT || e.status == SF_TRUNCATED))
             sd.steps += 1; /* a step that ran to its end (overflow / guard abort it midway) */
@@ -1240,14 +1367,12 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
             sd.ub_guards += e.status == SF_UB_GUARD;
             reset = k.auto_reset != 0;
         }
-        if (!reset) sf_store_env(d, env, e, false);
+        if (!reset) sf_store_env(d, env, e);
     }
     if (reset) { /* new behaviour: next episode of the synthetic seed chain */
-        int64_t ge = k.env_id_base + env;
         e.episode += 1;
-        e.draws = 0;
-        sf_reset_env(d, k, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode));
-        sf_store_env(d, env, e, true);
+        sf_reset_env(d, k, t, env, e);
+        sf_store_env(d, env, e);
     }
     SF_SYNCWARP();
 }

@@ -46,6 +46,7 @@ __device__ __forceinline__ void sf_stage_tables(const SfDev &d, SfTabs &t)
     t.exp_tab = reinterpret_cast<const uint16_t *>(sf_smem);
     t.smap = sf_smem + SF_SMEM_EXP;
     t.log_tab = d.log_tab;
+    t.rng_cst = d.rng_cst, t.E = d.E;
 }
 
 __device__ __forceinline__ void sf_flush_stats(const SfDev &d, const SfStatDelta &sd)
@@ -87,15 +88,27 @@ sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *
     sf_stage_tables(d, t);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = d.E >> 5;
+#ifdef SF_EXP_STATSEND
     SfStatDelta sd;
     memset(&sd, 0, sizeof sd);
+#endif
     for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
         int env = chunk * 32 + lane;
         bool valid = env < d.n_envs;
+#ifndef SF_EXP_STATSEND
+        SfStatDelta sd;
+        memset(&sd, 0, sizeof sd);
+#endif
         sf_step_body(d, k, t, env, valid, (actions && valid) ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);
+#ifndef SF_EXP_STATSEND
+        __syncwarp();
+        sf_flush_stats(d, sd);
+#endif
     }
+#ifdef SF_EXP_STATSEND
     __syncwarp();
     sf_flush_stats(d, sd);
+#endif
 }
 
 /* setup() + load_data() + _srand for the listed arenas (all when env_ids == NULL) */
@@ -128,6 +141,7 @@ __global__ void sf_synth_actions_kernel(uint8_t *actions, int n_envs, int n_agen
 __device__ __forceinline__ void sf_global_tabs(const SfDev &d, SfTabs &t)
 {
     t.exp_tab = d.exp_tab, t.log_tab = d.log_tab, t.smap = d.smap;
+    t.rng_cst = d.rng_cst, t.E = d.E;
 }
 
 __global__ void sf_hash_kernel(const SfDev d, const __grid_constant__ SfConst k, uint64_t *out)
@@ -237,10 +251,20 @@ sf_rng_kernel(const SfDev d, const int64_t *tb, const int64_t *serial, int n_str
     SfTabs t;
     sf_stage_tables(d, t);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_streams; i += gridDim.x * blockDim.x) {
-        SfEnv e;
-        e.draws = 0;
-        sf_srand(e, t, tb[i], serial[i]);
-        for (int j = 0; j < n_draws; ++j) out[(size_t)j * n_streams + i] = sf_rand(e, t);
+        /* stand-alone stream: seed, warm up and draw in registers (no arena state is touched) */
+        uint32_t Lp[9], c[18];
+        int64_t a = tb[i], b = serial[i];
+        for (int q = 0; q < 18; ++q) {
+            c[q] = (2u * (uint32_t)(a % 10 + 1)) | ((2u * (uint32_t)t.log_tab[(uint32_t)(b % 10)]) << 8);
+            a /= 10, b /= 10;
+        }
+        for (int q = 0; q < 9; ++q) Lp[q] = 0u;
+        uint32_t n = 0;
+        for (; n < SF_WARM_DRAWS; ++n) sf_warm_draw(t, Lp, c, n);
+        for (int j = 0; j < n_draws; ++j, ++n) {
+            sf_warm_draw(t, Lp, c, n);
+            out[(size_t)j * n_streams + i] = (int32_t)(((uint32_t)t.exp_tab[Lp[8] >> 16] + 1u) & 1023u);
+        }
     }
 }
 
@@ -311,11 +335,12 @@ void carve(Carver &c, sf_handle &h)
     c.take(d.frame, E), c.take(d.kills, E), c.take(d.tkills, E), c.take(d.loot, E), c.take(d.chest, E);
     c.take(d.misc, E), c.take(d.steps, E), c.take(d.episode, E), c.take(d.ntemp, E);
     c.take(d.mh, E), c.take(d.mz, 2 * E), c.take(d.mb, 2 * E), c.take(d.mp, 2 * E);
-    c.take(d.rng_log, 18 * E), c.take(d.rng_cst, 18 * E), c.take(d.jomle, E);
+    c.take(d.rng_log, 9 * E), c.take(d.rng_cst, 36 * E), c.take(d.rng_w, E), c.take(d.jomle, E);
+    c.take(d.pend_log, 9 * E), c.take(d.pend_n, E);
     size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)d.cap_t * E;
     c.take(d.h_pw, H), c.take(d.h_sel, H), c.take(d.h_bp, H), c.take(d.h_hp, H), c.take(d.h_mind, H);
     c.take(d.h_stam, H), c.take(d.h_kills, H), c.take(d.h_dmg, H), c.take(d.h_eff, H), c.take(d.h_cons, H);
-    c.take(d.h_thr, H);
+    c.take(d.h_thr, H), c.take(d.h_cmd, H);
     c.take(d.z_pos, Z), c.take(d.z_hp, Z), c.take(d.z_mind, Z);
     c.take(d.b_pw, B), c.take(d.b_meta, B), c.take(d.b_dmg, B), c.take(d.b_eff, B);
     c.take(d.t_cell, T), c.take(d.t_dmg, T), c.take(d.t_pidx, T);
@@ -472,8 +497,12 @@ int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb,
 static int sf_launch_step(sf_handle *h, int half, const uint8_t *d_actions, cudaStream_t s)
 {
     int nchunks = h->d.E / 32;
+#ifdef SF_EXP_OLDGRID
     int grid = (nchunks + SF_CTA / 32 - 1) / (SF_CTA / 32);
     if (grid > h->n_sm) grid = h->n_sm;
+#else
+    int grid = nchunks < h->n_sm ? nchunks : h->n_sm; /* one persistent CTA per SM; warps take chunks round-robin */
+#endif
     if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
     else if (half == SF_HALF_A) sf_step_kernel<SF_HALF_A><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, nullptr);
     else sf_step_kernel<SF_HALF_B><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);

@@ -108,18 +108,23 @@ typedef struct SfDev {
     /* header */
     uint32_t *frame;
     int32_t *kills, *tkills, *loot, *chest;
-    uint32_t *misc;    /* level | status << 8 | hw_h << 16 */
+    uint32_t *misc;    /* level | status << 8 | hw_h << 16 | fast-seed flag << 24 | rng_cst bank << 25 */
     uint32_t *steps, *episode, *ntemp;
     uint64_t *mh, *mz, *mb, *mp; /* live masks: mh[E], mz[2][E], mb[2][E], mp[2][E] */
     /* random.hpp state in the discrete-log domain */
-    uint16_t *rng_log;  /* [18][E] log_3(random[i]) */
-    uint32_t *rng_cst;  /* [18][E] 2*seed[i] | (2*log_3(us[i])) << 8 */
+    uint32_t *rng_log;  /* [9][E] log_3(random[2j]) | log_3(random[2j+1]) << 16 */
+    uint32_t *rng_cst;  /* [2][18][E] 2*seed[i] | (2*log_3(us[i])) << 8; bank = misc bit 25, the other
+                           bank belongs to the pending stream */
+    uint32_t *pend_log; /* [9][E] packed logs of the pending (next episode's) stream */
+    uint32_t *pend_n;   /* [E] warm-up draws made by the pending stream | fast flag << 16 */
+    uint32_t *rng_w;    /* [E] sum of the values random[10..17] */
     uint32_t *jomle;
     /* humans [cap_h][E] */
     uint16_t *h_pw, *h_sel;
     uint32_t *h_bp;    /* blocks | portals << 8 | (portal_ind + 1) << 16 */
     int32_t *h_hp, *h_mind, *h_stam, *h_kills, *h_dmg, *h_eff;
     uint32_t *h_cons, *h_thr;
+    uint8_t *h_cmd;    /* command[] between get_command and obey (gameplay.hpp:43, 979-1010) */
     /* zombies [cap_z][E] */
     uint16_t *z_pos;
     int32_t *z_hp, *z_mind;

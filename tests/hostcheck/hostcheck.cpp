@@ -49,12 +49,15 @@ HcHandle *hc_create(const sf_config *cfg)
     d.steps = h->alloc<uint32_t>(E), d.episode = h->alloc<uint32_t>(E), d.ntemp = h->alloc<uint32_t>(E);
     d.mh = h->alloc<uint64_t>(E), d.mz = h->alloc<uint64_t>(2 * E), d.mb = h->alloc<uint64_t>(2 * E);
     d.mp = h->alloc<uint64_t>(2 * E);
-    d.rng_log = h->alloc<uint16_t>(18 * E), d.rng_cst = h->alloc<uint32_t>(18 * E), d.jomle = h->alloc<uint32_t>(E);
+    d.rng_log = h->alloc<uint32_t>(9 * E), d.rng_cst = h->alloc<uint32_t>(36 * E), d.jomle = h->alloc<uint32_t>(E);
+    d.rng_w = h->alloc<uint32_t>(E);
+    d.pend_log = h->alloc<uint32_t>(9 * E), d.pend_n = h->alloc<uint32_t>(E);
     size_t H = (size_t)k.cap_h * E, Z = (size_t)k.cap_z * E, B = (size_t)k.cap_b * E, T = (size_t)d.cap_t * E;
     d.h_pw = h->alloc<uint16_t>(H), d.h_sel = h->alloc<uint16_t>(H), d.h_bp = h->alloc<uint32_t>(H);
     d.h_hp = h->alloc<int32_t>(H), d.h_mind = h->alloc<int32_t>(H), d.h_stam = h->alloc<int32_t>(H);
     d.h_kills = h->alloc<int32_t>(H), d.h_dmg = h->alloc<int32_t>(H), d.h_eff = h->alloc<int32_t>(H);
     d.h_cons = h->alloc<uint32_t>(H), d.h_thr = h->alloc<uint32_t>(H);
+    d.h_cmd = h->alloc<uint8_t>(H);
     d.z_pos = h->alloc<uint16_t>(Z), d.z_hp = h->alloc<int32_t>(Z), d.z_mind = h->alloc<int32_t>(Z);
     d.b_pw = h->alloc<uint16_t>(B), d.b_meta = h->alloc<uint32_t>(B), d.b_dmg = h->alloc<int32_t>(B);
     d.b_eff = h->alloc<int32_t>(B);
@@ -68,6 +71,7 @@ HcHandle *hc_create(const sf_config *cfg)
     sfhost::build_pow_lut(h->tabs, 1 << 16); /* small on purpose: exercises the beyond-table path */
     d.pow_lut = h->tabs.pow_lut.data(), d.pow_lut_len = (int32_t)h->tabs.pow_lut.size();
     h->t.smap = d.smap, h->t.exp_tab = d.exp_tab, h->t.log_tab = d.log_tab;
+    h->t.rng_cst = d.rng_cst, h->t.E = d.E;
     for (int env = 0; env < d.n_envs; ++env) {
         int64_t ge = k.env_id_base + env;
         sf_reset_body(d, k, h->t, env, sf_synth_tb(ge), sf_synth_serial(ge, 0), 0);

@@ -137,3 +137,65 @@ def test_step_host_matches_device_step(torch_cuda, arena_data):
         assert st["episodes"] == 64 * 2 and st["truncated"] + st["deaths"] + st["wins"] == st["episodes"]
     finally:
         a.close(), b.close()
+
+
+def test_golden_matches_through_the_c_abi(torch_cuda, arena_data):
+    """The reference's own trajectories (tests/golden, made by the unmodified reference) replayed on
+    the GPU: custom seeds through sf_reset, state hash after every step, observations bit for bit."""
+    import glob
+    import os
+    from strikeforce_b200.sim import BatchedArena
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for path in sorted(glob.glob(os.path.join(golden, "*.npz"))):
+        if path.endswith("kat.npz"):
+            continue
+        g = np.load(path)
+        sim = BatchedArena(33, mode=int(g["mode"]), level=int(g["level"]), squad_agents=bool(g["squad_agents"]),
+                           auto_reset=False, player=str(g["player"]))
+        try:
+            e = 32  # the last arena of a partly filled warp
+            sim.reset([e], [int(g["tb"])], [int(g["serial"])])
+            assert np.uint64(sim.state_hash()[e].item() & 0xFFFFFFFFFFFFFFFF) == g["hashes"][0]
+            obs = dict(zip(g["obs_steps"].tolist(), g["obs"]))
+            act = torch_cuda.full((33, sim.n_agents), ord("+"), dtype=torch_cuda.uint8, device=sim.device)
+            hashes = []
+            for t, a in enumerate(g["actions"]):
+                if t in obs:
+                    o = sim.observe(1)[e].reshape(-1).cpu().numpy()
+                    assert (o.view(np.uint32) == obs[t].view(np.uint32)).all(), "%s observation step %d" % (path, t)
+                act[e] = torch_cuda.from_numpy(a.copy()).to(sim.device)
+                sim.step(act)
+                hashes.append(sim.state_hash()[e:e + 1])
+            got = torch_cuda.cat(hashes).cpu().numpy().view(np.uint64)
+            bad = np.nonzero(got != g["hashes"][1:])[0]
+            assert len(bad) == 0, "%s: state differs from the reference at step %d" % (path, bad[0])
+            assert sim.step_out()[e, 0].item() == g["status"][-1]
+        finally:
+            sim.close()
+
+
+def test_auto_reset_chain_parity(torch_cuda, arena_data):
+    """Auto-reset installs the pending stream (short and long episodes) and follows sf_synth.h."""
+    from strikeforce_b200.sim import BatchedArena
+    for max_steps, steps in ((40, 130), (150, 320)):
+        n, base = 40, 1000
+        sim = BatchedArena(n, mode="Solo", level=1, auto_reset=True, max_steps=max_steps, env_id_base=base)
+        oracles = common.make_oracles(arena_data, n, sfcfg.MODE_SOLO, 1, max_steps=max_steps, env_id_base=base)
+        episode = [0] * n
+        try:
+            for t in range(steps):
+                act = sim.synth_actions(t, sfcfg.ACTIONS28)
+                act_h = act.cpu().numpy()
+                sim.step(act)
+                out = sim.step_out().cpu().numpy()
+                h = sim.state_hash().cpu().numpy().view(np.uint64)
+                for e, o in enumerate(oracles):
+                    st = o.step(bytes(act_h[e]))
+                    assert out[e, 0] == st
+                    if st != sfcfg.RUNNING:
+                        episode[e] += 1
+                        o.reset(1, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
+                    assert h[e] == np.uint64(o.state_hash()), "env %d step %d" % (e, t)
+            assert sim.stats()["episodes"] == sum(episode)
+        finally:
+            sim.close()

@@ -1,0 +1,118 @@
+"""The device tick (strikeforce_b200/csrc/sf_core.cuh) compiled for the host and compared with
+the C oracle -- a CPU-side check of the CUDA algorithm (layout, log-domain RNG, lock-step
+phases, observation features) for containers without a GPU.  The GPU tests repeat this
+through the real kernels and the C ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+import hostcheck
+import sfo
+from strikeforce_b200 import config as sfcfg
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not p.endswith("kat.npz"))
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_device_tick_matches_reference_golden(path, arena_data):
+    g = np.load(path)
+    cfg = sfcfg.make_config(arena_data, n_envs=2, mode=int(g["mode"]), level_min=int(g["level"]),
+                            squad_agents=bool(g["squad_agents"]), player=str(g["player"]), auto_reset=False)
+    hs = hostcheck.HostSim(cfg)
+    hs.reset(1, int(g["tb"]), int(g["serial"]))  # arena 1 plays the golden match, arena 0 another one
+    assert np.uint64(hs.state_hash(1)) == g["hashes"][0]
+    obs = dict(zip(g["obs_steps"].tolist(), g["obs"]))
+    idle = bytes(b"+" * hs.n_agents)
+    for t, act in enumerate(g["actions"]):
+        if t in obs:
+            assert (hs.observe(1, 0).view(np.uint32) == obs[t].view(np.uint32)).all(), "observation, step %d" % t
+        hs.step(idle + bytes(act))
+        assert hs.status(1) == g["status"][t], "status, step %d" % t
+        assert np.uint64(hs.state_hash(1)) == g["hashes"][t + 1], "state hash, step %d" % t
+
+
+def test_auto_reset_follows_the_seed_chain(arena_data):
+    """Episodes shorter and longer than the pending-stream warm-up (128 steps)."""
+    for max_steps, steps in ((40, 130), (150, 320)):
+        n, base = 3, 5
+        cfg = sfcfg.make_config(arena_data, n_envs=n, mode=sfcfg.MODE_SOLO, level_min=1, auto_reset=True,
+                                max_steps=max_steps, env_id_base=base)
+        hs = hostcheck.HostSim(cfg)
+        oracles = common.make_oracles(arena_data, n, sfcfg.MODE_SOLO, 1, max_steps=max_steps, env_id_base=base)
+        episode = [0] * n
+        for t in range(steps):
+            act = common.synth_actions(range(base, base + n), 1, t, sfcfg.ACTIONS28)
+            hs.step(act.tobytes())
+            for e, o in enumerate(oracles):
+                st = o.step(bytes(act[e]))
+                assert hs.step_out(e)["status"] == st
+                if st != sfcfg.RUNNING:
+                    episode[e] += 1
+                    o.reset(1, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
+                d0, d1 = o.dump(), hs.dump(e)
+                assert len(d0) == len(d1) and (d0 == d1).all(), sfo.diff_records(d0, d1)
+        assert hs.stats()["episodes"] == sum(episode) and hs.stats()["steps"] == n * steps
+
+
+def test_split_step_and_p2_observation(arena_data):
+    """sf_step_a / sf_step_b with the P2 observation point in between (gameplay.hpp:933)."""
+    cfg = sfcfg.make_config(arena_data, n_envs=1, mode=sfcfg.MODE_SQUAD, level_min=2, squad_agents=True, auto_reset=False)
+    hs = hostcheck.HostSim(cfg)
+    o = sfo.Arena(cfg)
+    o.reset(2, 1700000555, 777)
+    hs.reset(0, 1700000555, 777)
+    rng = np.random.default_rng(3)
+    for t in range(300):
+        act = bytes(sfcfg.ACTIONS9[i] for i in rng.integers(9, size=10))
+        o.step_a()
+        hs.step(None, half=1)
+        if o.status() != sfcfg.RUNNING:
+            break
+        if t % 25 == 0:
+            for slot in (1, 6):
+                try:
+                    ref = o.observe(slot)
+                except RuntimeError:
+                    continue
+                assert (hs.observe(0, slot).view(np.uint32) == ref.view(np.uint32)).all()
+        o.step_b(act)
+        hs.step(act, half=2)
+        assert hs.step_out(0) == o.step_out()
+        if o.status() != sfcfg.RUNNING:
+            break
+        d0, d1 = o.dump(), hs.dump(0)
+        assert len(d0) == len(d1) and (d0 == d1).all(), sfo.diff_records(d0, d1)
+
+
+def test_overflow_guard_and_truncation(arena_data):
+    caps = dict(cap_humans=12, cap_zombies=8, cap_bullets=6, cap_built=8, cap_portals=8)
+    n = 6
+    cfg = sfcfg.make_config(arena_data, n_envs=n, mode=sfcfg.MODE_SOLO, level_min=1, auto_reset=False, caps=caps,
+                            max_steps=250)
+    hs = hostcheck.HostSim(cfg)
+    oracles = common.make_oracles(arena_data, n, sfcfg.MODE_SOLO, 1, max_steps=250, caps=caps)
+    seen = set()
+    for t in range(260):
+        act = common.synth_actions(range(n), 1, t, sfcfg.ACTIONS28)
+        hs.step(act.tobytes())
+        for e, o in enumerate(oracles):
+            st = o.step(bytes(act[e]))
+            assert hs.status(e) == st
+            seen.add(st)
+            if st in (sfcfg.RUNNING, sfcfg.TRUNCATED, sfcfg.DEAD):
+                assert np.uint64(hs.state_hash(e)) == np.uint64(o.state_hash())
+    assert sfcfg.OVERFLOW in seen or sfcfg.TRUNCATED in seen
+
+
+def test_host_helpers_match_oracle():
+    L = hostcheck.lib()
+    for x in (0, 1, 2, 99, 100, 150, 225, 275, 1000, 1135, 4096, 65536, 1000000):
+        for y in (1, 2, 3, 50, 100, 255):
+            assert L.hc_compute_damage(x, y) == sfo.compute_damage(x, y)
+    for n in list(range(0, 3000, 7)) + [15000, 999999, 1000000, 1048575]:
+        assert np.float32(L.hc_obs_transform_milli(n)).view(np.uint32) == \
+            np.float32(sfo.obs_transform(np.float32(n / 1000.0))).view(np.uint32)

@@ -627,57 +627,6 @@ SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, i
     }
 }
 
-/* update_tmp, gameplay.hpp:1343-1381.  Four bullets per round (positions, then cells, loaded
- * together); whether a bullet is absorbed depends on the cell's kind and occupant only, which
- * no absorption changes, so the rounds need no forwarding. */
-SF_FN void sf_update_tmp(const SfDev &d, const SfConst &k, int env, SfEnv &e)
-{
-    const bool any = e.on && e.ntemp != 0; /* nothing player-built: no bullet can be absorbed */
-    const int hi = SF_WARP_MAX(any ? m2_highest(e.mb) : -1);
-    int hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0; /* cells that absorbed a bullet in this call */
-    int n_hit = 0;
-    for (int b0 = 0; b0 <= hi; b0 += 4) {
-        bool lv[4];
-        int cell[4];
-        uint32_t g[4];
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            lv[j] = any && b0 + j <= hi && m2_test(e.mb, b0 + j);
-            cell[j] = lv[j] ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
-        }
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            uint32_t kind = (g[j] >> C_KIND_SHIFT) & 7u;
-            if (lv[j] && (kind == K_BLOCK || (kind == K_ENTRANCE && !(g[j] & (C_S0 | C_S1))))) {
-                int q = sf_find_built(d, env, e, cell[j]);
-                SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b0 + j);
-                SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
-                m2_clear(e.mb, b0 + j);
-                if (n_hit == 0) hc0 = cell[j];
-                else if (n_hit == 1) hc1 = cell[j];
-                else if (n_hit == 2) hc2 = cell[j];
-                else if (n_hit == 3) hc3 = cell[j];
-                n_hit += 1;
-            }
-        }
-        SF_SYNCWARP();
-    }
-    /* a limit can only be crossed by an absorption of this very call (while a human hides an
-     * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
-    if (n_hit > 4) {
-        for (int q = (int)e.ntemp - 1; q >= 0; --q)
-            if (q < (int)e.ntemp) sf_check_built(d, k, env, e, SF_T(d.t_cell, q));
-    } else {
-        if (n_hit > 0) sf_check_built(d, k, env, e, hc0);
-        if (n_hit > 1) sf_check_built(d, k, env, e, hc1);
-        if (n_hit > 2) sf_check_built(d, k, env, e, hc2);
-        if (n_hit > 3) sf_check_built(d, k, env, e, hc3);
-    }
-    SF_SYNCWARP();
-}
-
 /* human_damage, gameplay.hpp:611-634 */
 SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int cell, uint32_t g, uint32_t meta)
 {
@@ -737,15 +686,85 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
     SF_G(cell) = (uint16_t)g;
 }
 
-/* hit_human + hit_zombie, gameplay.hpp:600-609, 636-652.  The reference walks every live
- * human / zombie and tests s[2] of its cell; a set s[2] always has exactly one owning
- * bullet, so walking the owning bullets and looking at who stands in their cell visits the
- * same (victim, bullet) pairs.  The pairs are independent (distinct victims, distinct
- * bullets, credits are sums), so their order does not matter. */
-SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
+/* update_tmp + hit_human + hit_zombie, gameplay.hpp:1343-1381, 600-609, 636-652, in ONE walk over
+ * the bullets (four per round: flags and positions, then cells, load together).
+ *
+ * update_tmp: a bullet standing on a player-built block, or on a player-built entrance that no
+ * human hides, is absorbed (the cell's dmg grows); then the touched cells are tested against
+ * lim_block / lim_portal.  Absorbing cells hold no human or zombie, so this never interferes
+ * with the hits.
+ * hit_human / hit_zombie: the reference walks every live human / zombie and tests s[2] of its
+ * cell; a set s[2] always has exactly one owning bullet, so walking the owning bullets and
+ * looking at who stands in their cell visits the same (victim, bullet) pairs, which are
+ * independent of each other (distinct victims, distinct bullets, credits are sums).
+ * Finally every owning bullet that hit nothing clears s[2] of its cell here: that is the
+ * themap1 snapshot of update_bull (:1061-1072, "s[2] = 0 on the current cell of every live
+ * bullet"), which nothing reads in between.  After this walk no cell has s[2] set. */
+SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
-    uint64_t q = e.on ? (e.quit & e.mh) : 0ull; /* first branch of hit_human: Hp <= 0, no bullet test */
+    const uint64_t quitters = e.on ? (e.quit & e.mh) : 0ull; /* Hp <= 0 by '_': removed, never hit (:640-645) */
     e.quit = 0;
+    const bool built_any = e.ntemp != 0;
+    int hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0; /* cells that absorbed a bullet in this call */
+    int n_hit = 0;
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
+    for (int b0 = 0; b0 <= hi; b0 += 4) {
+        bool lv[4];
+        uint32_t meta[4], g[4];
+        int cell[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            lv[j] = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
+            meta[j] = lv[j] ? SF_AT(d.b_meta, b0 + j) : 0u;
+            cell[j] = lv[j] ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            bool need = lv[j] && (built_any || (meta[j] & BF_OWNS));
+            g[j] = need ? (uint32_t)SF_G(cell[j]) : 0u;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            if (lv[j]) {
+                const int b = b0 + j;
+                uint32_t kind = (g[j] >> C_KIND_SHIFT) & 7u;
+                if (built_any && (kind == K_BLOCK || (kind == K_ENTRANCE && !(g[j] & (C_S0 | C_S1))))) {
+                    int q = sf_find_built(d, env, e, cell[j]);
+                    SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b);
+                    SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
+                    m2_clear(e.mb, b);
+                    if (n_hit == 0) hc0 = cell[j];
+                    else if (n_hit == 1) hc1 = cell[j];
+                    else if (n_hit == 2) hc2 = cell[j];
+                    else if (n_hit == 3) hc3 = cell[j];
+                    n_hit += 1;
+                } else if (meta[j] & BF_OWNS) {
+                    int occ = (int)(g[j] & C_OCC);
+                    if ((g[j] & C_S0) && ((e.mh >> occ) & 1) && !((quitters >> occ) & 1)) {
+                        sf_human_damage(d, env, e, occ, b, cell[j], g[j], meta[j]);
+                    } else if (g[j] & C_S1) {
+                        sf_zombie_damage(d, env, e, occ, b, cell[j], g[j], meta[j]);
+                    } else if (g[j] & C_S2) {
+                        SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
+                    }
+                }
+            }
+        }
+        SF_SYNCWARP();
+    }
+    /* a limit can only be crossed by an absorption of this very call (while a human hides an
+     * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
+    if (n_hit > 4) {
+        for (int q = (int)e.ntemp - 1; q >= 0; --q)
+            if (q < (int)e.ntemp) sf_check_built(d, k, env, e, SF_T(d.t_cell, q));
+    } else {
+        if (n_hit > 0) sf_check_built(d, k, env, e, hc0);
+        if (n_hit > 1) sf_check_built(d, k, env, e, hc1);
+        if (n_hit > 2) sf_check_built(d, k, env, e, hc2);
+        if (n_hit > 3) sf_check_built(d, k, env, e, hc3);
+    }
+    SF_SYNCWARP();
+    uint64_t q = quitters;
     const int nq = SF_WARP_MAX(sf_popc64(q));
     for (int i = 0; i < nq; ++i) {
         if (q) {
@@ -760,77 +779,20 @@ SF_FN void sf_hits(const SfDev &d, int env, SfEnv &e)
         }
         SF_SYNCWARP();
     }
-    /* four bullets per round: flags and positions, then the cells of the owners, load together;
-     * owners stand on distinct cells, so the rounds need no forwarding */
-    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
-    for (int b0 = 0; b0 <= hi; b0 += 4) {
-        bool own[4];
-        uint32_t meta[4], g[4];
-        int cell[4];
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            bool lv = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
-            meta[j] = lv ? SF_AT(d.b_meta, b0 + j) : 0u;
-            cell[j] = lv ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
-            own[j] = lv && (meta[j] & BF_OWNS);
-        }
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) g[j] = own[j] ? (uint32_t)SF_G(cell[j]) : 0u;
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            if (own[j]) {
-                if (g[j] & C_S0) {
-                    int h = (int)(g[j] & C_OCC);
-                    if ((e.mh >> h) & 1) sf_human_damage(d, env, e, h, b0 + j, cell[j], g[j], meta[j]);
-                } else if (g[j] & C_S1) {
-                    sf_zombie_damage(d, env, e, (int)(g[j] & C_OCC), b0 + j, cell[j], g[j], meta[j]);
-                }
-            }
-        }
-        SF_SYNCWARP();
-    }
 }
 
-/* update_bull, gameplay.hpp:1059-1100, plus the harness's out-of-bounds guard.  Pass 1 is the
- * themap1 snapshot with s[2] cleared on the current and next cell of every live bullet; pass 2
- * walks the bullets in the REVERSE of the reference's order so that the first bullet to reach
- * a cell here is the reference's last writer of it.  Both passes take four bullets per round:
- * positions, then cells, load together; pass 2 forwards a newly set s[2] to the later bullets
- * of its round. */
+/* update_bull, gameplay.hpp:1059-1100, plus the harness's out-of-bounds guard.  The snapshot
+ * half (s[2] cleared under every live bullet) was done by sf_resolve_bullets; here the bullets
+ * move, walked in the REVERSE of the reference's order so that the first bullet to reach a cell
+ * is the reference's last writer of it.  Four bullets per round (positions, then the cells
+ * ahead, load together); a newly set s[2] is forwarded to the later bullets of the round. */
 SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
-    bool oob = false;
-    for (int b0 = 0; b0 <= hi; b0 += 4) {
-        bool lv[4];
-        int cell[4], nc[4];
-        uint32_t g[4], gn[4];
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            lv[j] = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
-            uint32_t pw = lv[j] ? SF_AT(d.b_pw, b0 + j) : 0u;
-            cell[j] = (int)(pw & POS_CELL);
-            if (lv[j] && !sf_neighbour(cell[j], (int)(pw >> POS_HI_SHIFT), &nc[j])) {
-                oob = true; /* the reference would read themap[i][-1][k], :1069 */
-                lv[j] = false;
-            }
-        }
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
-            gn[j] = lv[j] ? (uint32_t)SF_G(nc[j]) : 0u;
-        }
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            if (g[j] & C_S2) SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
-            if (gn[j] & C_S2) SF_G(nc[j]) = (uint16_t)(gn[j] & ~C_S2);
-        }
-        SF_SYNCWARP();
-    }
-    if (oob) sf_fail_env(e, SF_UB_GUARD);
     int r = 0;
     if (e.on) r = sf_rand(e, t) & 1;
     SF_SYNCWARP();
+    bool oob = false;
     /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
@@ -842,10 +804,14 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
             lv[j] = e.on && i0 + j <= hi && m2_test(e.mb, b[j]);
             pw[j] = lv[j] ? SF_AT(d.b_pw, b[j]) : 0u;
             meta[j] = lv[j] ? (SF_AT(d.b_meta, b[j]) & ~BF_OWNS) : 0u;
-            nc[j] = (int)(pw[j] & POS_CELL) + sf_delta((int)(pw[j] >> POS_HI_SHIFT));
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
+            nc[j] = 0;
+            if (lv[j] && !sf_neighbour((int)(pw[j] & POS_CELL), (int)(pw[j] >> POS_HI_SHIFT), &nc[j])) {
+                oob = true; /* the reference would read themap[i][-1][k], :1069 */
+                lv[j] = false;
+            }
             bool expired = ((meta[j] >> 8) & 0xFFu) + 1 >= (meta[j] & 0xFFu); /* Bullet::expire, Item.hpp:165-168 */
             if (lv[j] && expired) {
                 m2_clear(e.mb, b[j]);
@@ -866,7 +832,7 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
                     SF_AT(d.b_meta, b[j]) = m + 0x100u;
                     SF_UNROLL
                     for (int jj = j + 1; jj < 4; ++jj)
-                        if (nc[jj] == nc[j]) gn[jj] |= C_S2;
+                        if (lv[jj] && nc[jj] == nc[j]) gn[jj] |= C_S2;
                 } else {
                     m2_clear(e.mb, b[j]);
                 }
@@ -874,6 +840,7 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
         }
         SF_SYNCWARP();
     }
+    if (oob) sf_fail_env(e, SF_UB_GUARD);
 }
 
 /* human_rnpc_bot, gameplay.hpp:1927-1940; returns the command symbol.  Written as a chain of
@@ -1214,8 +1181,7 @@ SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
     sf_spawns(d, k, t, env, e);
     sf_zombie_action(d, k, t, env, e);
     sf_portal_damage(d, k, env, e);
-    sf_update_tmp(d, k, env, e);
-    sf_hits(d, env, e);
+    sf_resolve_bullets(d, k, env, e);
     if (e.on) e.frame += 1;
     sf_update_bull(d, t, env, e);
 }
@@ -1224,8 +1190,7 @@ SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
 SF_FN void sf_step_b(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, const uint8_t *actions)
 {
     sf_human_action(d, k, t, env, e, actions);
-    sf_update_tmp(d, k, env, e);
-    sf_hits(d, env, e);
+    sf_resolve_bullets(d, k, env, e);
     if (e.on) e.frame += 1;
     sf_update_bull(d, t, env, e);
     if (e.on) e.steps += 1;

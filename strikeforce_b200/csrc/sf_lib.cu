@@ -409,6 +409,15 @@ int sf_create(const sf_config *cfg, sf_handle **out)
         delete h;
         return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 140,080 B)");
     }
+    /* The tick reads scattered 32-byte sectors (one cell of one arena at a time); the default
+       64-byte L2 fetch granularity doubles its DRAM read traffic for nothing.  Device-wide
+       limit; SF_L2_FETCH=0 leaves it alone, SF_L2_FETCH=64/128 overrides. */
+    {
+        const char *g = getenv("SF_L2_FETCH");
+        int gran = g ? atoi(g) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        cudaGetLastError();
+    }
     Carver sizer;
     carve(sizer, *h);
     h->arena_bytes = sizer.off + 256;

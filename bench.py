@@ -150,6 +150,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from strikeforce_b200 import config as sfcfg
+    from strikeforce_b200 import dist as sfdist
     from strikeforce_b200.sim import BatchedArena
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,12 +227,32 @@ def run_ours(args):
     ms_e2e_wall = (time.perf_counter() - w0) * 1e3
     ms_e2e = max(e0.elapsed_time(e1), ms_e2e_wall)
     st3 = sim.stats_tensor().clone()
+    # ---- second row: step + the player's observation tensor every step, on the device
+    obs_row = None
+    if not args.no_obs:
+        KO = max(2, K // 2)
+        obs_buf = torch.empty((E, 1, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32, device=sim.device)
+        acts_o = [sim.synth_actions(t + K + i, table, out=acts[i % K]) for i in range(KO)]
+        sim.observe(1, out=obs_buf)
+        eo = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        barrier()
+        eo[0].record()
+        for i in range(KO):
+            sim.observe(1, out=obs_buf)
+        eo[1].record()
+        for i in range(KO):
+            sim.observe(1, out=obs_buf)
+            sim.step(acts_o[i])
+        eo[2].record()
+        barrier()
+        ms_obs_only = eo[0].elapsed_time(eo[1])
+        ms_both = eo[1].elapsed_time(eo[2])
+        obs_row = (KO, ms_obs_only, ms_both)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
     # ---- reduce over ranks: max time, summed statistics (the only collective: NCCL all-reduce)
     local_algo = float((st1 - st0)[sfcfg.STAT_NAMES.index("algo_bytes")].item())
-    from strikeforce_b200 import dist as sfdist
     ms_dev = sfdist.max_over_ranks(ms_dev, sim.device)
     ms_e2e = sfdist.max_over_ranks(ms_e2e, sim.device)
     d_dev, d_e2e = sfdist.reduce_stats(st1 - st0), sfdist.reduce_stats(st3 - st2)
@@ -263,6 +284,16 @@ def run_ours(args):
                                                "ub_guards")},
             "rng_draws_per_env_step": d_dev["rng_draws"] / max(1, steps_done),
         }
+        if obs_row is not None:
+            KO, ms_obs_only, ms_both = obs_row
+            obs_bytes = E * sfcfg.OBS_LEN * 4
+            line["with_observation"] = {
+                "note": "rank 0; one fp32 [32,31,31] observation of the player per arena per step, written to HBM",
+                "value_step_plus_obs": KO * E / (ms_both / 1e3), "unit": UNIT, "ms_per_step": ms_both / KO,
+                "observe_kernel_ms": ms_obs_only / KO,
+                "roofline": {"bound": "hbm", "kernel": "sf_observe_kernel", "achieved": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9 / peak,
+                             "algo_bytes_per_observation": sfcfg.OBS_LEN * 4}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(args.cpu_steps)
         print(json.dumps(line))
@@ -309,6 +340,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=16384, help="env-steps per host core for cpu_baseline")
     ap.add_argument("--ref-steps", type=int, default=8192, help="env-steps per host core per reference-arm step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-obs", action="store_true", help="skip the step+observation row")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

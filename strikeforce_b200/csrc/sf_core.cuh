@@ -446,40 +446,54 @@ SF_FN int sf_exit_cell(const SfDev &d, const SfConst &k, int env, int idx)
  * "cell prints '.'" test, so they run as three rounds of one code path. */
 SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
+#pragma unroll 1
     for (int kind = 0; kind < 3; ++kind) {
         uint32_t period = kind == 0 ? 30u : kind == 1 ? 40u : 50u; /* pc, pz, ph: gameplay.hpp:459 */
         bool due = e.on && (e.frame % period <= 1u);
         if (kind == 0 && 9000 <= e.chest) due = false; /* C, gameplay.hpp:37 */
-        if (due) {
-            int i = sf_rand(e, t) % SF_FLOORS, j = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
-            int cell = sf_cell_of(i, j, c);
-            uint32_t g = SF_G(cell);
-            if (sf_showit(t.smap[cell], g) == SH_DOT) {
-                if (kind == 0) {
-                    int type = sf_rand(e, t) % 4;
-                    SF_G(cell) = (uint16_t)((K_CHEST0 + type) << C_KIND_SHIFT);
-                    e.chest += 1;
-                    if (e.chest > k.cap_chest) sf_fail_env(e, SF_OVERFLOW);
-                } else if (kind == 1) {
-                    int z = m2_lowest_free(e.mz);
-                    if (z >= k.cap_z) sf_fail_env(e, SF_OVERFLOW);
-                    else {
-                        int super_ = (sf_rand(e, t) % 4 == 0);
-                        SF_AT(d.z_pos, z) = (uint16_t)(cell | (super_ << POS_HI_SHIFT));
-                        SF_AT(d.z_hp, z) = (super_ + 1) * 400;
-                        SF_AT(d.z_mind, z) = (super_ + 1) * 100;
-                        SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
-                        m2_set(e.mz, z);
-                    }
-                } else {
-                    int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
-                    if (h < 0 || h >= k.cap_h) sf_fail_env(e, SF_OVERFLOW);
-                    else {
-                        sf_init_human(d, env, k.npc, h, cell, true, 0, false);
-                        SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)h);
-                        e.mh |= 1ull << h;
-                        if (h + 1 > e.hw_h) e.hw_h = h + 1;
-                    }
+        int i = 0, j = 0, c = 0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) { /* one draw site for floor, row, col */
+            if (due) {
+                int r = sf_rand(e, t);
+                if (q == 0) i = r % SF_FLOORS;
+                else if (q == 1) j = r % SF_ROWS;
+                else c = r % SF_COLS;
+            }
+        }
+        int cell = sf_cell_of(i, j, c);
+        bool dot = false;
+        if (due) dot = sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT;
+        int z = 0;
+        if (dot && kind == 1) {
+            z = m2_lowest_free(e.mz);
+            if (z >= k.cap_z) {
+                sf_fail_env(e, SF_OVERFLOW);
+                dot = false;
+            }
+        }
+        int extra = 0;
+        if (dot && kind < 2) extra = sf_rand(e, t) % 4; /* chest type / "is it a super zombie" */
+        if (dot) {
+            if (kind == 0) {
+                SF_G(cell) = (uint16_t)((K_CHEST0 + extra) << C_KIND_SHIFT);
+                e.chest += 1;
+                if (e.chest > k.cap_chest) sf_fail_env(e, SF_OVERFLOW);
+            } else if (kind == 1) {
+                int super_ = (extra == 0);
+                SF_AT(d.z_pos, z) = (uint16_t)(cell | (super_ << POS_HI_SHIFT));
+                SF_AT(d.z_hp, z) = (super_ + 1) * 400;
+                SF_AT(d.z_mind, z) = (super_ + 1) * 100;
+                SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
+                m2_set(e.mz, z);
+            } else {
+                int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
+                if (h < 0 || h >= k.cap_h) sf_fail_env(e, SF_OVERFLOW);
+                else {
+                    sf_init_human(d, env, k.npc, h, cell, true, 0, false);
+                    SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)h);
+                    e.mh |= 1ull << h;
+                    if (h + 1 > e.hw_h) e.hw_h = h + 1;
                 }
             }
         }
@@ -547,26 +561,34 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                 }
                 wander = !adjacent && e.on;
             }
-            if (wander) wander = !(sf_rand(e, t) % 5 < 2);
-            for (int i1 = 0; i1 < 2; ++i1) {
-                if (wander) {
-                    int i2 = sf_rand(e, t) % 4;
-                    int nc = cell[j] + sf_delta(i2);
-                    uint32_t gn = i2 == 0 ? gv[j][1] : i2 == 1 ? gv[j][2] : i2 == 2 ? gv[j][3] : gv[j][4];
-                    if (sf_showit(t.smap[nc], gn) == SH_DOT) {
-                        uint32_t vnew = C_S1 | (uint32_t)z, vold = gv[j][0] & ~(C_S1 | C_OCC);
-                        SF_G(nc) = (uint16_t)vnew;
-                        SF_G(cell[j]) = (uint16_t)vold;
-                        SF_AT(d.z_pos, z) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc);
-                        if (j == 0) {
-                            if (cell[1] == nc) gv[1][0] = vnew;
-                            SF_UNROLL
-                            for (int c = 0; c < 4; ++c) {
-                                if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = vnew;
-                                if (cell[1] + sf_delta(c) == cell[0]) gv[1][1 + c] = vold;
+            /* one draw site: stage 0 = "stay put?" (rand()%5 < 2), stages 1, 2 = the two tries */
+            int stage = wander ? 0 : 3;
+#pragma unroll 1
+            for (int it = 0; it < 3; ++it) {
+                if (stage < 3) {
+                    int r = sf_rand(e, t);
+                    if (stage == 0) {
+                        stage = (r % 5 < 2) ? 3 : 1;
+                    } else {
+                        int i2 = r % 4;
+                        int nc = cell[j] + sf_delta(i2);
+                        uint32_t gn = i2 == 0 ? gv[j][1] : i2 == 1 ? gv[j][2] : i2 == 2 ? gv[j][3] : gv[j][4];
+                        stage = stage == 1 ? 2 : 3;
+                        if (sf_showit(t.smap[nc], gn) == SH_DOT) {
+                            uint32_t vnew = C_S1 | (uint32_t)z, vold = gv[j][0] & ~(C_S1 | C_OCC);
+                            SF_G(nc) = (uint16_t)vnew;
+                            SF_G(cell[j]) = (uint16_t)vold;
+                            SF_AT(d.z_pos, z) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc);
+                            if (j == 0) {
+                                if (cell[1] == nc) gv[1][0] = vnew;
+                                SF_UNROLL
+                                for (int c = 0; c < 4; ++c) {
+                                    if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = vnew;
+                                    if (cell[1] + sf_delta(c) == cell[0]) gv[1][1 + c] = vold;
+                                }
                             }
+                            stage = 3;
                         }
-                        wander = false;
                     }
                 }
             }
@@ -758,10 +780,9 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
         for (int q = (int)e.ntemp - 1; q >= 0; --q)
             if (q < (int)e.ntemp) sf_check_built(d, k, env, e, SF_T(d.t_cell, q));
     } else {
-        if (n_hit > 0) sf_check_built(d, k, env, e, hc0);
-        if (n_hit > 1) sf_check_built(d, k, env, e, hc1);
-        if (n_hit > 2) sf_check_built(d, k, env, e, hc2);
-        if (n_hit > 3) sf_check_built(d, k, env, e, hc3);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i)
+            if (i < n_hit) sf_check_built(d, k, env, e, i == 0 ? hc0 : i == 1 ? hc1 : i == 2 ? hc2 : hc3);
     }
     SF_SYNCWARP();
     uint64_t q = quitters;
@@ -847,18 +868,32 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
  * "does this lane still need a draw" steps so that the lanes of a warp stay together. */
 SF_FN int sf_rnpc_bot(const SfTabs &t, SfEnv &e, bool want)
 {
+    /* the key rows of the reference, eight symbols to a 64-bit constant */
+    const uint64_t weapons = 0x2f2e2c6d6e627663ull; /* "cvbnm,./" */
+    const uint64_t moves = 0x0070647377613231ull;   /* "12awsdp"  */
+    const uint64_t others = 0x5d5b6a686766752bull;  /* "+ufghj[]" */
     int c = '+';
-    bool pick_weapon = want && (e.frame % 50 <= 1);
-    bool more = want && !pick_weapon;
-    /* the key rows of the reference are packed eight symbols to a 64-bit constant */
-    if (pick_weapon) c = (int)((0x2f2e2c6d6e627663ull >> (8 * (sf_rand(e, t) % 8))) & 0xFFu); /* "cvbnm,./" */
-    if (more && sf_rand(e, t) % 5 < 3) c = 'x', more = false;
+    /* stage 0: rand()%5 < 3 -> 'x'; 1: rand()%5 < 3 -> moves; 2: pick from a row; 3: weapon key; 4: done */
+    int stage = want ? ((e.frame % 50 <= 1) ? 3 : 0) : 4;
     bool second = false;
-    if (more) second = sf_rand(e, t) % 5 < 3;
-    if (more) {
-        int r = sf_rand(e, t);
-        c = second ? (int)((0x0070647377613231ull >> (8 * (r % 7))) & 0xFFu)  /* "12awsdp" */
-                   : (int)((0x5d5b6a686766752bull >> (8 * (r % 8))) & 0xFFu); /* "+ufghj[]" */
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        if (stage < 4) {
+            int r = sf_rand(e, t);
+            if (stage == 3) {
+                c = (int)((weapons >> (8 * (r % 8))) & 0xFFu);
+                stage = 4;
+            } else if (stage == 0) {
+                if (r % 5 < 3) c = 'x', stage = 4;
+                else stage = 1;
+            } else if (stage == 1) {
+                second = r % 5 < 3;
+                stage = 2;
+            } else {
+                c = second ? (int)((moves >> (8 * (r % 7))) & 0xFFu) : (int)((others >> (8 * (r % 8))) & 0xFFu);
+                stage = 4;
+            }
+        }
     }
     return c;
 }
@@ -1175,26 +1210,30 @@ SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
     SF_SYNCWARP();
 }
 
-/* first half of the loop body: spawns and half-tick A, gameplay.hpp:1444-1461 */
-SF_FN void sf_step_a(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+/* The loop body of gameplay::play(), gameplay.hpp:1444-1471, then the victory test.  Both
+ * half-ticks end with the same three calls (update_tmp, hit_human / hit_zombie, ++frame,
+ * update_bull), so they run as two rounds of one loop: round 0 = spawns + zombie_action +
+ * portal_damage (:1444-1456), round 1 = human_action (:1464). */
+SF_FN void sf_step_halves(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e,
+                          const uint8_t *actions, int first, int last)
 {
-    sf_spawns(d, k, t, env, e);
-    sf_zombie_action(d, k, t, env, e);
-    sf_portal_damage(d, k, env, e);
-    sf_resolve_bullets(d, k, env, e);
-    if (e.on) e.frame += 1;
-    sf_update_bull(d, t, env, e);
-}
-
-/* second half: human_action and half-tick B, gameplay.hpp:1462-1471, then the victory test */
-SF_FN void sf_step_b(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, const uint8_t *actions)
-{
-    sf_human_action(d, k, t, env, e, actions);
-    sf_resolve_bullets(d, k, env, e);
-    if (e.on) e.frame += 1;
-    sf_update_bull(d, t, env, e);
-    if (e.on) e.steps += 1;
-    sf_eval_end(d, k, env, e);
+#pragma unroll 1
+    for (int ph = first; ph <= last; ++ph) {
+        if (ph == 0) {
+            sf_spawns(d, k, t, env, e);
+            sf_zombie_action(d, k, t, env, e);
+            sf_portal_damage(d, k, env, e);
+        } else {
+            sf_human_action(d, k, t, env, e, actions);
+        }
+        sf_resolve_bullets(d, k, env, e);
+        if (e.on) e.frame += 1;
+        sf_update_bull(d, t, env, e);
+    }
+    if (last == 1) {
+        if (e.on) e.steps += 1;
+        sf_eval_end(d, k, env, e);
+    }
 }
 
 /* ------------------------------------------------------------------ header load / store */
@@ -1304,11 +1343,8 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         o.d_hp -= SF_AT(d.h_hp, 0), o.d_damage -= SF_AT(d.h_dmg, 0), o.d_effect -= SF_AT(d.h_eff, 0);
         d.out[env] = o;
     }
-    if (half != SF_HALF_B) {
-        if (e.on) sd.algo_bytes += sf_algo_bytes(k, e);
-        sf_step_a(d, k, t, env, e);
-    }
-    if (half != SF_HALF_A) sf_step_b(d, k, t, env, e, actions);
+    if (half != SF_HALF_B && e.on) sd.algo_bytes += sf_algo_bytes(k, e);
+    sf_step_halves(d, k, t, env, e, actions, half == SF_HALF_B ? 1 : 0, half == SF_HALF_A ? 0 : 1);
     if (valid) {
         /* a terminal arena that is not auto-reset waits for sf_reset: report, change nothing */
         sf_step_out o = d.out[env];

@@ -235,11 +235,18 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
     __syncthreads();
     uint32_t fb = 0;
     for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
-        int32_t f[32];
         int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
-        sf_describe_milli(d, k, t, env, e, cell, team, bmap[w], tmap[w], f);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[c], &fb);
+        /* most of a window is floor or lies outside the map: 32 zeros, transform(0) = 0 */
+        bool empty = cell < 0 || (t.smap[cell] == 0 && SF_G(cell) == 0);
+        if (empty) {
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = 0.f;
+        } else {
+            int32_t f[32];
+            sf_describe_milli(d, k, t, env, e, cell, team, bmap[w], tmap[w], f);
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[c], &fb);
+        }
     }
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }

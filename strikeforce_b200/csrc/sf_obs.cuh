@@ -125,19 +125,30 @@ SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, 
     if (s0) f[30] = SF_AT(d.h_dmg, occ), f[31] = -SF_AT(d.h_eff, occ);
 }
 
+/* beyond the host-built table: the device's pow (counted by the caller; it may differ from
+ * the host libm in the last bit).  Out of line on purpose: inlined 32 times it evicts the
+ * whole observation kernel from the instruction cache. */
+#ifdef __CUDACC__
+__device__ __noinline__ float sf_obs_transform_slow(uint32_t a)
+{
+    float x = (float)((double)a / 1000.0);
+    return (float)pow((double)(x / 10.0f), 0.2);
+}
+#else
+static float sf_obs_transform_slow(uint32_t a)
+{
+    float x = (float)((double)a / 1000.0);
+    return (float)__builtin_pow((double)(x / 10.0f), 0.2);
+}
+#endif
+
 /* float(pow(double(float(m / 1000.0) / 10), 0.2)): host-built table, device pow beyond it */
 SF_FN float sf_obs_transform(const SfDev &d, int32_t m, uint32_t *fallbacks)
 {
     uint32_t a = m < 0 ? (uint32_t)(-(int64_t)m) : (uint32_t)m;
     if (a < (uint32_t)d.pow_lut_len) return d.pow_lut[a];
     *fallbacks += 1;
-#ifdef __CUDA_ARCH__
-    float x = (float)((double)a / 1000.0);
-    return (float)pow((double)(x / 10.0f), 0.2);
-#else
-    float x = (float)((double)a / 1000.0);
-    return (float)__builtin_pow((double)(x / 10.0f), 0.2);
-#endif
+    return sf_obs_transform_slow(a);
 }
 
 /* window cell (wi, wj) of a viewer standing on `vcell` -> map cell or -1 (Custom.hpp:144-150) */

@@ -188,66 +188,116 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
     o[5] = __popcll(SF_AT(d.mp, 0)) + __popcll(SF_AT(d.mp, 1));
 }
 
-/* gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158): one CTA per
- * (arena, selected human).  Stores are channel-major, 4 B per thread, consecutive threads on
- * consecutive window cells, so every warp store is a run of 128 contiguous bytes. */
-#define SF_OBS_CTA 256
-__global__ void __launch_bounds__(SF_OBS_CTA)
-sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
-                  int nsel)
+/* gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158).
+ *
+ * The product is 123,008 contiguous bytes per (arena, observer), almost all zeros (floor, cells
+ * outside the map) -- a pure HBM-write problem.  Persistent CTAs (five per SM, so that the
+ * load latency of one overlaps the stores of the others) build each observation in shared
+ * memory, 8 channels (30,752 B) at a time, and hand the tile to the TMA engine with
+ * cp.async.bulk (shared -> global, bulk-group completion): the stores are whole aligned lines.
+ *   1. entity -> window maps for the owning bullets and player-built cells (shared memory);
+ *   2. the window is classified; cells that are neither floor nor outside the map go to a
+ *      work list, so the per-cell feature code runs on dense lanes (~15% of a window);
+ *   3. per tile: wait until the TMA has read the tile's previous content, zero it, write the
+ *      features of the listed cells, fence to the async proxy, one thread issues the bulk store. */
+#ifndef SF_OBS_CTA
+#define SF_OBS_CTA 128
+#define SF_OBS_CTAS_PER_SM 5
+#define SF_OBS_HALF_CH 8 /* channels per shared-memory tile (measured: 16/256/3 -> 46%, 8/128/5 -> 51% of HBM peak) */
+#endif
+#define SF_OBS_HALF_FLOATS (SF_OBS_HALF_CH * SF_OBS_CELLS) /* 15,376 floats = 61,504 B, a multiple of 16 */
+#define SF_OBS_SMEM (SF_OBS_HALF_FLOATS * 4 + 3 * 1984 + 16)
+
+__device__ __forceinline__ void sf_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
 {
-    __shared__ int16_t bmap[SF_OBS_CELLS], tmap[SF_OBS_CELLS];
-    const int env = blockIdx.x / nsel;
-    int a = blockIdx.x % nsel;
-    uint32_t m = agent_mask;
-    for (int i = 0; i < a; ++i) m &= m - 1;
-    const int slot = __ffs(m) - 1;
-    float *out = obs + (size_t)blockIdx.x * SF_OBS_LEN;
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(SF_OBS_CTA, SF_OBS_CTAS_PER_SM)
+sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
+                  int nsel, int n_items)
+{
+    float *tile = reinterpret_cast<float *>(sf_smem);
+    int16_t *bmap = reinterpret_cast<int16_t *>(sf_smem + SF_OBS_HALF_FLOATS * 4);
+    int16_t *tmap = bmap + 992;
+    uint16_t *work = reinterpret_cast<uint16_t *>(tmap + 992);
+    int *count = reinterpret_cast<int *>(work + 992);
     SfTabs t;
     sf_global_tabs(d, t);
-    SfEnv e;
-    sf_load_env(d, env, e);
-    if (slot >= e.hw_h) { /* a human slot this episode never used: no observer */
-        for (int i = threadIdx.x; i < SF_OBS_LEN; i += SF_OBS_CTA) out[i] = 0.f;
-        return;
-    }
-    const int vcell = (int)(SF_AT(d.h_pw, slot) & POS_CELL);
-    const uint32_t team = SF_AT(d.h_sel, slot) & HS_TEAM;
-    const int fbase = (vcell / (SF_ROWS * SF_COLS)) * (SF_ROWS * SF_COLS);
-    const int r0 = sf_row_of(vcell) - SF_OBS_R, c0 = sf_col_of(vcell) - SF_OBS_R;
-    for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
-    __syncthreads();
-    for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
-        if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
-            int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL) - fbase;
-            if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
-                int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
-                if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN) bmap[wi * SF_OBS_WIN + wj] = (int16_t)b;
+    uint32_t fb = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int env = item / nsel;
+        uint32_t m = agent_mask;
+        for (int i = item % nsel; i > 0; --i) m &= m - 1;
+        const int slot = __ffs(m) - 1;
+        float *out = obs + (size_t)item * SF_OBS_LEN;
+        /* the few header words the features need */
+        SfEnv e;
+        const uint32_t misc = d.misc[env];
+        e.level = (int)(misc & 0xFFu), e.hw_h = (int)((misc >> 16) & 0xFFu);
+        e.mb[0] = SF_AT(d.mb, 0), e.mb[1] = SF_AT(d.mb, 1);
+        e.ntemp = d.ntemp[env];
+        e.env = env;
+        const bool observer = slot < e.hw_h; /* a slot this episode never used sees nothing */
+        const int vcell = observer ? (int)(SF_AT(d.h_pw, slot) & POS_CELL) : 0;
+        const uint32_t team = observer ? (SF_AT(d.h_sel, slot) & HS_TEAM) : 0u;
+        const int fbase = (vcell / (SF_ROWS * SF_COLS)) * (SF_ROWS * SF_COLS);
+        const int r0 = sf_row_of(vcell) - SF_OBS_R, c0 = sf_col_of(vcell) - SF_OBS_R;
+        for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
+        if (threadIdx.x == 0) *count = 0;
+        __syncthreads();
+        if (observer) {
+            for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
+                if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
+                    int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL) - fbase;
+                    if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
+                        int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
+                        if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
+                            bmap[wi * SF_OBS_WIN + wj] = (int16_t)b;
+                    }
+                }
+            for (int q = threadIdx.x; q < (int)e.ntemp; q += SF_OBS_CTA) {
+                int cell = (int)SF_T(d.t_cell, q) - fbase;
+                if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
+                    int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
+                    if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
+                        tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
+                }
+            }
+            for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
+                int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+                if (cell >= 0 && (t.smap[cell] != 0 || SF_G(cell) != 0)) work[atomicAdd(count, 1)] = (uint16_t)w;
             }
         }
-    for (int q = threadIdx.x; q < (int)e.ntemp; q += SF_OBS_CTA) {
-        int cell = (int)SF_T(d.t_cell, q) - fbase;
-        if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
-            int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
-            if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN) tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
+        __syncthreads();
+        const int n_work = *count;
+#pragma unroll
+        for (int part = 0; part < SF_OBS_CH / SF_OBS_HALF_CH; ++part) {
+            float *half = tile;
+            /* the TMA must have read the tile's previous content before it is overwritten */
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            float4 *h4 = reinterpret_cast<float4 *>(half);
+            for (int i = threadIdx.x; i < SF_OBS_HALF_FLOATS / 4; i += SF_OBS_CTA) h4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_work; i += SF_OBS_CTA) {
+                const int w = work[i];
+                int32_t f[32];
+                sf_describe_milli(d, k, t, env, e, sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN), team, bmap[w],
+                                  tmap[w], f);
+#pragma unroll
+                for (int c = 0; c < SF_OBS_HALF_CH; ++c)
+                    half[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[part * SF_OBS_HALF_CH + c], &fb);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> async proxy */
+            __syncthreads();
+            if (threadIdx.x == 0) sf_bulk_store(out + part * SF_OBS_HALF_FLOATS, half, SF_OBS_HALF_FLOATS * 4);
+            static_assert((SF_OBS_HALF_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
         }
     }
-    __syncthreads();
-    uint32_t fb = 0;
-    for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
-        int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
-        /* most of a window is floor or lies outside the map: 32 zeros, transform(0) = 0 */
-        bool empty = cell < 0 || (t.smap[cell] == 0 && SF_G(cell) == 0);
-        if (empty) {
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = 0.f;
-        } else {
-            int32_t f[32];
-            sf_describe_milli(d, k, t, env, e, cell, team, bmap[w], tmap[w], f);
-#pragma unroll 4
-            for (int c = 0; c < 32; ++c) out[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[c], &fb);
-        }
-    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }
 
@@ -460,6 +510,7 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_step_kernel<SF_HALF_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_rng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_OBS_SMEM));
     rc = sf_launch_reset(h, nullptr, h->d.n_envs, nullptr, nullptr, 0);
     if (rc == SF_OK) {
         cudaError_t e_ = cudaDeviceSynchronize();
@@ -578,8 +629,11 @@ int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, voi
     if (phase != SF_OBS_P1 && phase != SF_OBS_P2) return sf_fail(h, SF_ERR_ARG, "sf_observe: phase must be SF_OBS_P1 or SF_OBS_P2");
     int nsel = __builtin_popcount(agent_mask);
     if (nsel == 0) return sf_fail(h, SF_ERR_ARG, "sf_observe: empty agent mask");
-    sf_observe_kernel<<<h->d.n_envs * nsel, SF_OBS_CTA, 0, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
-                                                                                               nsel);
+    if (reinterpret_cast<uintptr_t>(obs) & 15u) return sf_fail(h, SF_ERR_ARG, "sf_observe: obs must be 16-byte aligned");
+    int n_items = h->d.n_envs * nsel;
+    int grid = n_items < SF_OBS_CTAS_PER_SM * h->n_sm ? n_items : SF_OBS_CTAS_PER_SM * h->n_sm;
+    sf_observe_kernel<<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
+                                                                                          nsel, n_items);
     h->launches += 1;
     SF_CUDA(h, cudaGetLastError());
     return SF_OK;

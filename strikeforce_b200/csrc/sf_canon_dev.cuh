@@ -51,10 +51,11 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
     for (int h = 0; h < e.hw_h; ++h) {
         uint32_t pw = SF_AT(d.h_pw, h), sel = SF_AT(d.h_sel, h), bp = SF_AT(d.h_bp, h);
         uint32_t cp = SF_AT(d.h_cons, h), tp = SF_AT(d.h_thr, h);
-        int cell = (int)(pw & POS_CELL), n = 0;
+        int n = 0, pf, pr, pc;
+        sf_tcell_decode((int)(pw & POS_CELL), &pf, &pr, &pc);
         f[n++] = (int32_t)((e.mh >> h) & 1), f[n++] = (sel & HS_RNPC) ? 1 : 0, f[n++] = (int32_t)(sel & HS_TEAM);
         f[n++] = (int32_t)(pw >> POS_HI_SHIFT) + 1;
-        f[n++] = cell / (SF_ROWS * SF_COLS), f[n++] = sf_row_of(cell), f[n++] = sf_col_of(cell);
+        f[n++] = pf, f[n++] = pr, f[n++] = pc;
         f[n++] = SF_AT(d.h_hp, h), f[n++] = SF_AT(d.h_mind, h), f[n++] = SF_AT(d.h_stam, h);
         f[n++] = SF_AT(d.h_kills, h), f[n++] = SF_AT(d.h_dmg, h), f[n++] = SF_AT(d.h_eff, h);
         f[n++] = (int32_t)((sel >> HS_VEC_SHIFT) & 3u) - 1, f[n++] = (int32_t)((sel >> HS_IND_SHIFT) & 15u) - 1;
@@ -66,15 +67,17 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
     }
     for (int z = m2_next(e.mz, 0); z >= 0; z = m2_next(e.mz, z + 1)) {
         uint32_t pw = SF_AT(d.z_pos, z);
-        int cell = (int)(pw & POS_CELL);
-        f[0] = (int32_t)(pw >> POS_HI_SHIFT), f[1] = cell / (SF_ROWS * SF_COLS), f[2] = sf_row_of(cell);
-        f[3] = sf_col_of(cell), f[4] = SF_AT(d.z_hp, z), f[5] = SF_AT(d.z_mind, z);
+        int pf, pr, pc;
+        sf_tcell_decode((int)(pw & POS_CELL), &pf, &pr, &pc);
+        f[0] = (int32_t)(pw >> POS_HI_SHIFT), f[1] = pf, f[2] = pr;
+        f[3] = pc, f[4] = SF_AT(d.z_hp, z), f[5] = SF_AT(d.z_mind, z);
         sink.elem(SF_K_ZOMBIE, z, f, SF_NF_ZOMBIE);
     }
     for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1)) {
         uint32_t pw = SF_AT(d.b_pw, b), meta = SF_AT(d.b_meta, b);
-        int cell = (int)(pw & POS_CELL), way0 = (int)(pw >> POS_HI_SHIFT), trav = (int)((meta >> 8) & 0xFFu);
-        int fl = cell / (SF_ROWS * SF_COLS), r = sf_row_of(cell), c = sf_col_of(cell);
+        int way0 = (int)(pw >> POS_HI_SHIFT), trav = (int)((meta >> 8) & 0xFFu);
+        int fl, r, c;
+        sf_tcell_decode((int)(pw & POS_CELL), &fl, &r, &c);
         f[0] = fl, f[1] = r, f[2] = c;
         f[3] = fl, f[4] = r - trav * ((way0 == 0) - (way0 == 2)), f[5] = c - trav * ((way0 == 1) - (way0 == 3));
         f[6] = way0 + 1, f[7] = (int32_t)(meta & 0xFFu), f[8] = SF_AT(d.b_dmg, b), f[9] = SF_AT(d.b_eff, b);
@@ -82,11 +85,11 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         sink.elem(SF_K_BULLET, b, f, SF_NF_BULLET);
     }
     for (int p = m2_next(e.mp, 0); p >= 0; p = m2_next(e.mp, p + 1)) {
-        int cell = sf_exit_cell(d, k, env, p);
-        f[0] = cell / (SF_ROWS * SF_COLS), f[1] = sf_row_of(cell), f[2] = sf_col_of(cell);
+        sf_tcell_decode(sf_exit_cell(d, k, env, p), &f[0], &f[1], &f[2]);
         sink.elem(SF_K_PORTAL, p, f, SF_NF_PORTAL);
     }
-    for (int cell = 0; cell < SF_CELLS; ++cell) {
+    for (int lin = 0; lin < SF_CELLS; ++lin) { /* the record lists cells in the reference's (floor, row, col) order */
+        const int cell = sf_tcell(lin / (SF_ROWS * SF_COLS), (lin / SF_COLS) % SF_ROWS, lin % SF_COLS);
         uint32_t g = SF_G(cell);
         if (!g) continue;
         uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
@@ -103,7 +106,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         f[4] = (g & C_S2) ? 1 : 0, f[5] = bidx;
         f[6] = chest ? 1 : 0, f[7] = chest ? (int32_t)kind - K_CHEST0 : -1;
         f[8] = built, f[9] = q >= 0 ? SF_T(d.t_dmg, q) : 0, f[10] = built == 2 ? (int32_t)SF_T(d.t_pidx, q) : -1;
-        sink.elem(SF_K_CELL, cell, f, SF_NF_CELL);
+        sink.elem(SF_K_CELL, lin, f, SF_NF_CELL);
     }
 }
 

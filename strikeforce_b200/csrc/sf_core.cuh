@@ -43,7 +43,7 @@
 
 /* tables every lane reads: shared memory on the device, plain arrays in the host check */
 struct SfTabs {
-    const uint8_t *smap;     /* static map bytes [SF_CELLS] */
+    const uint8_t *smap;     /* static map bytes [SF_TCELLS], tiled cell ids */
     const uint16_t *exp_tab; /* [65536] */
     const uint16_t *log_tab; /* [65536] */
     const uint32_t *rng_cst; /* [2][18][E] per-arena term constants (terms 10..17 are read on demand) */
@@ -145,18 +145,26 @@ SF_FN int m2_prev(const uint64_t m[2], int i)
 #define SF_T(arr, q) (arr)[(size_t)env * (size_t)d.cap_t + (size_t)(q)]
 #define SF_G(cell) d.grid[(size_t)env * SF_GRID_STRIDE + (size_t)(cell)]
 
-SF_FN int sf_cell_of(int f, int r, int c) { return (f * SF_ROWS + r) * SF_COLS + c; }
-SF_FN int sf_row_of(int cell) { return (cell / SF_COLS) % SF_ROWS; }
-SF_FN int sf_col_of(int cell) { return cell % SF_COLS; }
-/* wdx / wdy, gameplay.hpp:459: way-1 = 0 down(+row) 1 right(+col) 2 up 3 left */
-SF_FN int sf_delta(int d) { return d == 0 ? SF_COLS : d == 1 ? 1 : d == 2 ? -SF_COLS : -1; }
+SF_FN int sf_cell_of(int f, int r, int c) { return sf_tcell(f, r, c); }
+/* the neighbour of a (tiled) cell id, no bounds test; wdx / wdy, gameplay.hpp:459:
+ * way-1 = 0 down(+row) 1 right(+col) 2 up 3 left.  Inside a tile rows are 8 ids apart and
+ * columns 1; the next tile to the right starts 32 ids later, the one below 13 * 32 later. */
+SF_FN int sf_step_cell(int t, int d)
+{
+    const int inr = (t >> 3) & 3, inc = t & 7;
+    if (d == 0) return inr != 3 ? t + 8 : t + SF_TILES_X * 32 - 24;
+    if (d == 1) return inc != 7 ? t + 1 : t + 32 - 7;
+    if (d == 2) return inr != 0 ? t - 8 : t - SF_TILES_X * 32 + 24;
+    return inc != 0 ? t - 1 : t - 32 + 7;
+}
 /* neighbour in direction d with the bounds test obey() makes (gameplay.hpp:704, 747, 801) */
 SF_FN bool sf_neighbour(int cell, int d, int *out)
 {
-    int r = sf_row_of(cell), c = sf_col_of(cell);
+    int f, r, c;
+    sf_tcell_decode(cell, &f, &r, &c);
     r += (d == 0) - (d == 2);
     c += (d == 1) - (d == 3);
-    *out = cell + sf_delta(d);
+    *out = sf_step_cell(cell, d);
     return !(r >= SF_ROWS || r < 0 || c >= SF_COLS || c < 0);
 }
 
@@ -528,7 +536,7 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
             if (act[j]) {
                 gv[j][0] = SF_G(cell[j]);
                 SF_UNROLL
-                for (int i1 = 0; i1 < 4; ++i1) gv[j][1 + i1] = SF_G(cell[j] + sf_delta(i1));
+                for (int i1 = 0; i1 < 4; ++i1) gv[j][1 + i1] = SF_G(sf_step_cell(cell[j], i1));
             }
         }
         SF_UNROLL
@@ -546,14 +554,14 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                         if (!(gn & C_S2) && e.on) {
                             int b = sf_alloc_bullet(k, e);
                             if (b >= 0) {
-                                int nc = cell[j] + sf_delta(i1);
+                                int nc = sf_step_cell(cell[j], i1);
                                 int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
                                 sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
                                 if (j == 0) { /* forward the new s[2] to the second zombie's copy */
                                     if (cell[1] == nc) gv[1][0] = gn | C_S2;
                                     SF_UNROLL
                                     for (int c = 0; c < 4; ++c)
-                                        if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = gn | C_S2;
+                                        if (sf_step_cell(cell[1], c) == nc) gv[1][1 + c] = gn | C_S2;
                                 }
                             }
                         }
@@ -571,7 +579,7 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                         stage = (r % 5 < 2) ? 3 : 1;
                     } else {
                         int i2 = r % 4;
-                        int nc = cell[j] + sf_delta(i2);
+                        int nc = sf_step_cell(cell[j], i2);
                         uint32_t gn = i2 == 0 ? gv[j][1] : i2 == 1 ? gv[j][2] : i2 == 2 ? gv[j][3] : gv[j][4];
                         stage = stage == 1 ? 2 : 3;
                         if (sf_showit(t.smap[nc], gn) == SH_DOT) {
@@ -583,8 +591,8 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                                 if (cell[1] == nc) gv[1][0] = vnew;
                                 SF_UNROLL
                                 for (int c = 0; c < 4; ++c) {
-                                    if (cell[1] + sf_delta(c) == nc) gv[1][1 + c] = vnew;
-                                    if (cell[1] + sf_delta(c) == cell[0]) gv[1][1 + c] = vold;
+                                    if (sf_step_cell(cell[1], c) == nc) gv[1][1 + c] = vnew;
+                                    if (sf_step_cell(cell[1], c) == cell[0]) gv[1][1 + c] = vold;
                                 }
                             }
                             stage = 3;
@@ -1130,7 +1138,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
 
 /* ------------------------------------------------------------------ reset */
 
-/* one arena's overlay is 18,016 bytes, a multiple of 16 and 16-byte aligned */
+/* one arena's overlay is 19,968 bytes, a multiple of 64 and 64-byte aligned */
 SF_FN void sf_clear_grid(uint16_t *g)
 {
 #ifdef __CUDA_ARCH__

@@ -139,14 +139,15 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     k.cap_t = cfg.cap_built, k.cap_p = cfg.cap_portals;
     k.env_id_base = cfg.env_id_base;
     /* static map, gameplay.hpp:1252-1274: exits get portal indices in scan order */
-    t.smap.assign(SF_CELLS, 0);
+    t.smap.assign(SF_TCELLS, M_WALL); /* tiled cell ids (sf_state.h); padding cells read as walls */
     int n_exit = 0;
-    for (int id = 0; id < SF_CELLS; ++id) {
-        char c = (char)cfg.map_cells[id];
+    for (int lin = 0; lin < SF_CELLS; ++lin) {
+        const int id = sf_tcell(lin / (SF_ROWS * SF_COLS), (lin / SF_COLS) % SF_ROWS, lin % SF_COLS);
+        char c = (char)cfg.map_cells[lin];
         uint8_t m = 0;
         if (c == '#') m = M_WALL;
         else if (c == '^' || c == 'v') {
-            int tgt = cfg.map_portal[id];
+            int tgt = cfg.map_portal[lin];
             if (tgt < 0 || tgt >= SF_MAX_STATIC_EXITS) return "portal entrance target out of range";
             m = (uint8_t)((c == '^' ? M_UP : M_DOWN) | (tgt << M_TARGET_SHIFT));
         } else if (c == 'O') {
@@ -159,7 +160,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     }
     k.n_static_exits = n_exit;
     if (n_exit >= cfg.cap_portals) return "cap_portals must exceed the number of static exits";
-    for (int id = 0; id < SF_CELLS; ++id)
+    for (int id = 0; id < SF_TCELLS; ++id)
         if ((t.smap[id] & (M_UP | M_DOWN)) && (t.smap[id] >> M_TARGET_SHIFT) >= n_exit)
             return "portal entrance without an exit";
     /* the engine reads the four neighbours of zombies and the cell ahead of bullets without a
@@ -168,7 +169,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
         for (int r = 0; r < SF_ROWS; ++r)
             for (int c = 0; c < SF_COLS; ++c)
                 if (r == 0 || c == 0 || r == SF_ROWS - 1 || c == SF_COLS - 1) {
-                    uint8_t m = t.smap[(f * SF_ROWS + r) * SF_COLS + c];
+                    uint8_t m = t.smap[sf_tcell(f, r, c)];
                     if (!(m & (M_WALL | M_UP | M_DOWN))) return "arena border must be closed";
                 }
     for (int i = 0; i < 4; ++i) k.cons[i] = cfg.consumables[i];

@@ -26,7 +26,7 @@
 #define SF_CTA 1024 /* threads per CTA = arenas in flight per SM (one CTA per SM) */
 #endif
 #define SF_SMEM_EXP 131072
-#define SF_SMEM_MAP 9008
+#define SF_SMEM_MAP SF_TCELLS /* 9,984, a multiple of 16 */
 #define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP)
 #define SF_POW_LUT_LEN (1 << 21)
 #define SF_EXPORT_CAP (1 << 18)
@@ -243,28 +243,27 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         const bool observer = slot < e.hw_h; /* a slot this episode never used sees nothing */
         const int vcell = observer ? (int)(SF_AT(d.h_pw, slot) & POS_CELL) : 0;
         const uint32_t team = observer ? (SF_AT(d.h_sel, slot) & HS_TEAM) : 0u;
-        const int fbase = (vcell / (SF_ROWS * SF_COLS)) * (SF_ROWS * SF_COLS);
-        const int r0 = sf_row_of(vcell) - SF_OBS_R, c0 = sf_col_of(vcell) - SF_OBS_R;
+        int vf, vr, vc;
+        sf_tcell_decode(vcell, &vf, &vr, &vc);
+        const int r0 = vr - SF_OBS_R, c0 = vc - SF_OBS_R;
         for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
         if (threadIdx.x == 0) *count = 0;
         __syncthreads();
         if (observer) {
             for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
                 if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
-                    int cell = (int)(SF_AT(d.b_pw, b) & POS_CELL) - fbase;
-                    if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
-                        int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
-                        if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
-                            bmap[wi * SF_OBS_WIN + wj] = (int16_t)b;
-                    }
+                    int bf, br, bc;
+                    sf_tcell_decode((int)(SF_AT(d.b_pw, b) & POS_CELL), &bf, &br, &bc);
+                    int wi = br - r0, wj = bc - c0;
+                    if (bf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
+                        bmap[wi * SF_OBS_WIN + wj] = (int16_t)b;
                 }
             for (int q = threadIdx.x; q < (int)e.ntemp; q += SF_OBS_CTA) {
-                int cell = (int)SF_T(d.t_cell, q) - fbase;
-                if (cell >= 0 && cell < SF_ROWS * SF_COLS) {
-                    int wi = cell / SF_COLS - r0, wj = cell % SF_COLS - c0;
-                    if (wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
-                        tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
-                }
+                int tf, tr, tc;
+                sf_tcell_decode((int)SF_T(d.t_cell, q), &tf, &tr, &tc);
+                int wi = tr - r0, wj = tc - c0;
+                if (tf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
+                    tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
             }
             for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
                 int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
@@ -465,15 +464,6 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     if (smem_optin < SF_SMEM_BYTES) {
         delete h;
         return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 140,080 B)");
-    }
-    /* The tick reads scattered 32-byte sectors (one cell of one arena at a time); the default
-       64-byte L2 fetch granularity doubles its DRAM read traffic for nothing.  Device-wide
-       limit; SF_L2_FETCH=0 leaves it alone, SF_L2_FETCH=64/128 overrides. */
-    {
-        const char *g = getenv("SF_L2_FETCH");
-        int gran = g ? atoi(g) : 32;
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
-        cudaGetLastError();
     }
     Carver sizer;
     carve(sizer, *h);

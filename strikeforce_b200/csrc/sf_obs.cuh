@@ -154,9 +154,11 @@ SF_FN float sf_obs_transform(const SfDev &d, int32_t m, uint32_t *fallbacks)
 /* window cell (wi, wj) of a viewer standing on `vcell` -> map cell or -1 (Custom.hpp:144-150) */
 SF_FN int sf_obs_cell(int vcell, int wi, int wj)
 {
-    int r = sf_row_of(vcell) - SF_OBS_R + wi, c = sf_col_of(vcell) - SF_OBS_R + wj;
+    int f, r, c;
+    sf_tcell_decode(vcell, &f, &r, &c);
+    r += wi - SF_OBS_R, c += wj - SF_OBS_R;
     if (r < 0 || c < 0 || SF_ROWS <= r || SF_COLS <= c) return -1;
-    return (vcell / (SF_ROWS * SF_COLS)) * (SF_ROWS * SF_COLS) + r * SF_COLS + c;
+    return sf_tcell(f, r, c);
 }
 
 #endif

@@ -31,7 +31,32 @@
 
 #include "strikeforce_b200.h"
 
-#define SF_GRID_STRIDE 9008 /* SF_CELLS rounded up to a multiple of 16 cells (32 B sectors) */
+/* Cell ids on the device are TILED: the map is cut into tiles of 4 rows x 8 columns (32 cells =
+ * 64 bytes of overlay, the granule in which L2 fetches from HBM), 13 x 8 tiles per floor, so the
+ * four neighbours of a cell usually lie in the same granule (a row-major grid needs three).
+ * id = tile << 5 | (row & 3) << 3 | (col & 7), tile = (floor * 8 + row / 4) * 13 + col / 8.
+ * Cells of the padding rows 30, 31 and columns 100..103 are never referenced. */
+#define SF_TILES_X 13
+#define SF_TILES_Y 8
+#define SF_TCELLS (SF_FLOORS * SF_TILES_Y * SF_TILES_X * 32) /* 9,984 */
+#define SF_GRID_STRIDE SF_TCELLS
+
+#ifdef __CUDACC__
+#define SF_HDI __host__ __device__ __forceinline__
+#else
+#define SF_HDI static inline
+#endif
+SF_HDI int sf_tcell(int f, int r, int c)
+{
+    return ((((f * SF_TILES_Y + (r >> 2)) * SF_TILES_X + (c >> 3)) << 5) | ((r & 3) << 3) | (c & 7));
+}
+SF_HDI void sf_tcell_decode(int t, int *f, int *r, int *c)
+{
+    int tile = t >> 5, trow = tile / SF_TILES_X, tcol = tile - trow * SF_TILES_X;
+    *f = trow >> 3;
+    *r = ((trow & 7) << 2) | ((t >> 3) & 3);
+    *c = (tcol << 3) | (t & 7);
+}
 
 /* cell overlay bits */
 #define C_OCC 0x00FFu
@@ -144,7 +169,7 @@ typedef struct SfDev {
     sf_step_out *out;
     unsigned long long *stats; /* [SF_STAT_COUNT] */
     /* shared tables in global memory */
-    const uint8_t *smap;      /* [SF_CELLS] static map bytes */
+    const uint8_t *smap;      /* [SF_TCELLS] static map bytes, tiled like the overlay */
     const uint16_t *exp_tab;  /* [65536] 3^k mod 65537, minus one */
     const uint16_t *log_tab;  /* [65536] log_3(v) for v = index + 1 */
     const float *pow_lut;     /* observation transform, see sf_observe */

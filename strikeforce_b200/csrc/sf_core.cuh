@@ -379,12 +379,13 @@ SF_FN int sf_alloc_bullet(const SfConst &k, SfEnv &e)
 SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, uint32_t g, int way0, int range,
                            int owner, int dmg, int eff)
 {
-    if (g & C_S2) {
-        int hi = m2_highest(e.mb);
-        for (int o = 0; o <= hi; ++o) {
-            if (o != b && m2_test(e.mb, o)) {
-                uint32_t m = SF_AT(d.b_meta, o);
-                if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) SF_AT(d.b_meta, o) = m & ~BF_OWNS;
+    if (g & C_S2) { /* rare, and always inside divergent code: a plain early-exit walk over the live bullets */
+        for (int o = m2_next(e.mb, 0); o >= 0; o = m2_next(e.mb, o + 1)) {
+            if (o == b) continue;
+            uint32_t m = SF_AT(d.b_meta, o);
+            if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) {
+                SF_AT(d.b_meta, o) = m & ~BF_OWNS;
+                break;
             }
         }
     }
@@ -404,17 +405,18 @@ SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
     /* the per-arena record block is 16-byte aligned (cap_t is a multiple of 8) */
     const uint4 *tv = reinterpret_cast<const uint4 *>(tc);
     const uint32_t want = (uint32_t)cell;
-    for (uint32_t q0 = 0; q0 < e.ntemp; q0 += 8) {
+    /* callers are rare events inside divergent code, so the walk may stop at the first hit */
+    for (uint32_t q0 = 0; q0 < e.ntemp && found < 0; q0 += 8) {
         uint4 v = tv[q0 >> 3];
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
         SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            if ((w[j] & 0xFFFFu) == want && q0 + 2 * j < e.ntemp) found = (int)(q0 + 2 * j);
+        for (int j = 3; j >= 0; --j) {
             if ((w[j] >> 16) == want && q0 + 2 * j + 1 < e.ntemp) found = (int)(q0 + 2 * j + 1);
+            if ((w[j] & 0xFFFFu) == want && q0 + 2 * j < e.ntemp) found = (int)(q0 + 2 * j);
         }
     }
 #else
-    for (uint32_t q = 0; q < e.ntemp; ++q)
+    for (uint32_t q = 0; q < e.ntemp && found < 0; ++q)
         if (tc[q] == cell) found = (int)q;
 #endif
     return found;
@@ -915,91 +917,94 @@ SF_FN int sf_key_index(int c, int group)
          : c == '.' ? 6 : c == '/' ? 7 : -1;
 }
 
-/* obey + teleport + claim_chest for one human, gameplay.hpp:695-821, 517-530, 507-515 */
+/* obey + teleport + claim_chest for one human, gameplay.hpp:695-821, 517-530, 507-515.
+ * Everything a command can need -- the human's own cell, the one cell it can act on (ahead
+ * for '[' ']' 'z' 'x', in the walking direction for 'a' 's' 'd' 'w'), and its selection, stamina
+ * and mindamage when it fires or consumes -- is loaded up front in one round of independent
+ * loads; the rules then run on registers. */
 SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c)
 {
     uint32_t pw = SF_AT(d.h_pw, h);
     int cell = (int)(pw & POS_CELL);
     int way0 = (int)(pw >> POS_HI_SHIFT);
+    const bool acts_ahead = c == '[' || c == ']' || c == 'z' || c == 'x';
+    const bool walks = c == 'a' || c == 's' || c == 'd' || c == 'w';
+    const int dir = acts_ahead ? way0 : c == 's' ? 0 : c == 'd' ? 1 : c == 'w' ? 2 : 3;
+    int nc = cell;
+    const bool inb = (acts_ahead || walks) && sf_neighbour(cell, dir, &nc);
+    const bool uses_kit = c == 'x' || c == 'z' || c == 'u';
+    uint32_t g = SF_G(cell);
+    uint32_t gn = inb ? (uint32_t)SF_G(nc) : 0u;
+    uint32_t sel = uses_kit ? (uint32_t)SF_AT(d.h_sel, h) : 0u;
+    int st = uses_kit ? SF_AT(d.h_stam, h) : 0;
+    int md = uses_kit ? SF_AT(d.h_mind, h) : 0;
+    const int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
     if (c == '_') {
         SF_AT(d.h_hp, h) = 0;
         e.quit |= 1ull << h;
     } else if (c == '[' || c == ']') {
-        int nc;
-        if (sf_neighbour(cell, way0, &nc)) {
-            uint32_t gn = SF_G(nc);
-            if (sf_showit(t.smap[nc], gn) == SH_DOT) {
-                uint32_t bp = SF_AT(d.h_bp, h);
-                uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
-                if (c == '[') {
-                    if (blocks && sf_push_built(d, k, env, e, nc, 0)) {
-                        SF_G(nc) = (uint16_t)(K_BLOCK << C_KIND_SHIFT);
-                        SF_AT(d.h_bp, h) = bp - 1u;
-                    }
-                } else if (pend) { /* second press: the entrance bound to the pending exit */
-                    if (sf_push_built(d, k, env, e, nc, (int)pend - 1)) {
-                        SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
-                        SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
-                    }
-                } else if (portals) { /* first press: the exit, lowest free portal slot (p_ind) */
-                    int pi = m2_lowest_free(e.mp);
-                    if (pi >= k.cap_p) sf_fail_env(e, SF_OVERFLOW);
-                    else if (sf_push_built(d, k, env, e, nc, 0)) {
-                        SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
-                        SF_AT(d.p_cell, pi) = (uint16_t)nc;
-                        m2_set(e.mp, pi);
-                        SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);
-                    }
+        if (inb && sf_showit(t.smap[nc], gn) == SH_DOT) {
+            uint32_t bp = SF_AT(d.h_bp, h);
+            uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
+            if (c == '[') {
+                if (blocks && sf_push_built(d, k, env, e, nc, 0)) {
+                    SF_G(nc) = (uint16_t)(K_BLOCK << C_KIND_SHIFT);
+                    SF_AT(d.h_bp, h) = bp - 1u;
+                }
+            } else if (pend) { /* second press: the entrance bound to the pending exit */
+                if (sf_push_built(d, k, env, e, nc, (int)pend - 1)) {
+                    SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
+                    SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
+                }
+            } else if (portals) { /* first press: the exit, lowest free portal slot (p_ind) */
+                int pi = m2_lowest_free(e.mp);
+                if (pi >= k.cap_p) sf_fail_env(e, SF_OVERFLOW);
+                else if (sf_push_built(d, k, env, e, nc, 0)) {
+                    SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
+                    SF_AT(d.p_cell, pi) = (uint16_t)nc;
+                    m2_set(e.mp, pi);
+                    SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);
                 }
             }
         }
     } else if (c == 'q' || c == 'e') { /* turn_l: way+1, turn_r: way-1, Character.hpp:745-759 */
         way0 = (c == 'e') ? ((way0 + 3) & 3) : ((way0 + 1) & 3);
-        pw = (uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT);
-        SF_AT(d.h_pw, h) = (uint16_t)pw;
-    } else if (c == 'a' || c == 's' || c == 'd' || c == 'w') {
-        int dir = c == 's' ? 0 : c == 'd' ? 1 : c == 'w' ? 2 : 3;
-        int nc;
-        if (sf_neighbour(cell, dir, &nc)) {
-            uint32_t gn = SF_G(nc);
+        SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
+    } else if (walks) {
+        if (inb) {
             int sit = sf_showit(t.smap[nc], gn);
             if (sit == SH_CHEST || sit == SH_UP || sit == SH_DOWN || sit == SH_DOT || sit == SH_BULLET) {
-                SF_G(nc) = (uint16_t)((gn & ~C_OCC) | C_S0 | (uint32_t)h);
-                SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
+                gn = (gn & ~C_OCC) | C_S0 | (uint32_t)h;
+                SF_G(nc) = (uint16_t)gn;
+                SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
                 cell = nc;
-                pw = (uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT);
-                SF_AT(d.h_pw, h) = (uint16_t)pw;
+                g = gn;
+                SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
             }
         }
     } else if (c == 'u') { /* Human::use, Character.hpp:379-389 */
-        uint32_t sel = SF_AT(d.h_sel, h);
-        int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
         if (vec == 0) {
             uint32_t cp = SF_AT(d.h_cons, h);
             uint32_t cnt = (cp >> (8 * ind)) & 0xFFu;
             if (cnt >= 1) {
-                SF_AT(d.h_stam, h) += k.cons[ind].stamina;
+                SF_AT(d.h_stam, h) = st + k.cons[ind].stamina;
                 SF_AT(d.h_hp, h) += k.cons[ind].hp;
-                SF_AT(d.h_mind, h) += k.cons[ind].effect;
+                SF_AT(d.h_mind, h) = md + k.cons[ind].effect;
                 SF_AT(d.h_cons, h) = cp - (1u << (8 * ind));
                 if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT)); /* vec = -1 */
             }
         }
     } else if (c == 'z' || c == 'x') {
-        int nc;
         int b = m2_lowest_free(e.mb); /* b_ind() comes first, :800 */
-        if (sf_neighbour(cell, way0, &nc)) {
-            uint32_t sel = SF_AT(d.h_sel, h);
-            int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
+        if (inb) {
             bool can = false;
             int dmg = 0, eff = 0, range = 1;
             if (c == 'z') { /* Human::punch, Character.hpp:391-397 */
-                int md = SF_AT(d.h_mind, h), pb = sf_punch_base(k, e, h);
+                int pb = sf_punch_base(k, e, h);
                 dmg = pb > md ? pb : md;
                 can = true;
             } else if (vec == 1) { /* Human::throw_it, Character.hpp:410-427 */
                 const SfWpn w = sf_tmpl(k, h).thr[ind];
-                int md = SF_AT(d.h_mind, h), st = SF_AT(d.h_stam, h);
                 dmg = w.damage > w.damage + md ? w.damage : w.damage + md;
                 eff = w.effect, range = w.range;
                 if (st + w.stamina >= 0) {
@@ -1017,9 +1022,8 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             } else if (vec == 2) { /* Human::shot_it, Character.hpp:399-408 */
                 const SfTemplate &tp = sf_tmpl(k, h);
                 const SfWpn w = tp.wpn[ind];
-                int st = SF_AT(d.h_stam, h);
                 if (st + w.stamina >= 0) {
-                    int md = SF_AT(d.h_mind, h), sb = tp.shot_base[ind];
+                    int sb = tp.shot_base[ind];
                     SF_AT(d.h_stam, h) = st + w.stamina;
                     dmg = sb > w.damage + md ? sb : w.damage + md;
                     eff = w.effect, range = w.range;
@@ -1027,7 +1031,6 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                 }
             }
             if (can) {
-                uint32_t gn = SF_G(nc);
                 int sit = sf_showit(t.smap[nc], gn);
                 bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
                 if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
@@ -1043,37 +1046,37 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         int i;
         if ((i = sf_key_index(c, 0)) >= 0) {
             if ((SF_AT(d.h_cons, h) >> (8 * i)) & 0xFFu) {
-                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(sel | (1u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (1u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         } else if ((i = sf_key_index(c, 1)) >= 0) {
             if ((SF_AT(d.h_thr, h) >> (8 * i)) & 0xFFu) {
-                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(sel | (2u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (2u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         } else if ((i = sf_key_index(c, 2)) >= 0) {
             if ((sf_tmpl(k, h).w_owned >> i) & 1u) {
-                uint32_t sel = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(sel | (3u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
+                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (3u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         }
     }
     if (e.on) {
-        /* teleport, gameplay.hpp:517-530 */
-        uint32_t g = SF_G(cell);
-        uint32_t st = t.smap[cell];
+        /* teleport, gameplay.hpp:517-530 (g is the current content of the human's cell) */
+        uint32_t stc = t.smap[cell];
         int pidx = -1;
-        if (st & (M_UP | M_DOWN)) pidx = (int)(st >> M_TARGET_SHIFT);
+        if (stc & (M_UP | M_DOWN)) pidx = (int)(stc >> M_TARGET_SHIFT);
         else if (((g >> C_KIND_SHIFT) & 7u) == K_ENTRANCE) pidx = SF_T(d.t_pidx, sf_find_built(d, env, e, cell));
         if (pidx >= 0) {
             int dc = sf_exit_cell(d, k, env, pidx);
             uint32_t gd = SF_G(dc);
             if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
-                SF_G(dc) = (uint16_t)((gd & ~C_OCC) | C_S0 | (uint32_t)h);
+                gd = (gd & ~C_OCC) | C_S0 | (uint32_t)h;
+                SF_G(dc) = (uint16_t)gd;
                 SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
                 cell = dc;
+                g = gd;
                 SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
-                g = SF_G(cell);
             }
         }
         /* claim_chest, gameplay.hpp:507-515, Human::claim_chest Character.hpp:372-377 */

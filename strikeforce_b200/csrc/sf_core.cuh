@@ -1102,9 +1102,6 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     const uint64_t live = e.on ? e.mh : 0ull;
     const int hi = SF_WARP_MAX(live ? sf_fls64(live) : -1);
     const int cmd0 = (actions && e.on) ? actions[0] : '+';
-#ifdef SF_EXP_CMDLOCAL
-    uint8_t cmdl[SF_LIM_HUMANS];
-#endif
     for (int h = 1; h <= hi; ++h) {
         bool is_live = (live >> h) & 1;
         uint32_t sel = is_live ? SF_AT(d.h_sel, h) : 0u;
@@ -1118,11 +1115,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
                 if (!ok) c = '+';
             }
         }
-#ifdef SF_EXP_CMDLOCAL
-        cmdl[h] = (uint8_t)c;
-#else
         if (is_live) SF_AT(d.h_cmd, h) = (uint8_t)c;
-#endif
         SF_SYNCWARP();
     }
     int r = 0;
@@ -1130,11 +1123,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     SF_SYNCWARP();
     for (int i = 0; i <= hi; ++i) {
         int h = r ? i : hi - i;
-#ifdef SF_EXP_CMDLOCAL
-        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, h == 0 ? cmd0 : (int)cmdl[h]);
-#else
         if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h));
-#endif
         SF_SYNCWARP();
     }
 }

@@ -23,7 +23,7 @@
 #include "sf_obs.cuh"
 
 #ifndef SF_CTA
-#define SF_CTA 1024 /* threads per CTA = arenas in flight per SM (one CTA per SM) */
+#define SF_CTA 896 /* threads per CTA = arenas in flight per SM (one CTA per SM); 28 warps x 148 SMs = 4144 >= the 4096 chunks of 131072 arenas, 72 registers per thread */
 #endif
 #define SF_SMEM_EXP 131072
 #define SF_SMEM_MAP SF_TCELLS /* 9,984, a multiple of 16 */
@@ -88,27 +88,15 @@ sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *
     sf_stage_tables(d, t);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = d.E >> 5;
-#ifdef SF_EXP_STATSEND
-    SfStatDelta sd;
-    memset(&sd, 0, sizeof sd);
-#endif
     for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
         int env = chunk * 32 + lane;
         bool valid = env < d.n_envs;
-#ifndef SF_EXP_STATSEND
         SfStatDelta sd;
         memset(&sd, 0, sizeof sd);
-#endif
         sf_step_body(d, k, t, env, valid, (actions && valid) ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);
-#ifndef SF_EXP_STATSEND
         __syncwarp();
         sf_flush_stats(d, sd);
-#endif
     }
-#ifdef SF_EXP_STATSEND
-    __syncwarp();
-    sf_flush_stats(d, sd);
-#endif
 }
 
 /* setup() + load_data() + _srand for the listed arenas (all when env_ids == NULL) */
@@ -554,12 +542,7 @@ int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb,
 static int sf_launch_step(sf_handle *h, int half, const uint8_t *d_actions, cudaStream_t s)
 {
     int nchunks = h->d.E / 32;
-#ifdef SF_EXP_OLDGRID
-    int grid = (nchunks + SF_CTA / 32 - 1) / (SF_CTA / 32);
-    if (grid > h->n_sm) grid = h->n_sm;
-#else
     int grid = nchunks < h->n_sm ? nchunks : h->n_sm; /* one persistent CTA per SM; warps take chunks round-robin */
-#endif
     if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
     else if (half == SF_HALF_A) sf_step_kernel<SF_HALF_A><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, nullptr);
     else sf_step_kernel<SF_HALF_B><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);

@@ -100,6 +100,8 @@ def cpu_reference(steps_per_arena, passes=1, with_obs=False):
 # ----------------------------------------------------------------------------- clocks sampler
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled through NVML while the timed regions run
+    (the timed region lasts tens of milliseconds: nvidia-smi, ~100 ms per call, is only the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -107,34 +109,69 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.max_sm, self.reasons = [], [], set()
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.max_sm.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 9:
+                self.sm.append(float(r[1]))
+                self.max_sm.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002 if self.nvml is not None else 0.2)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(self.sm) if self.sm else None, sm_max_mhz=max(self.max_sm) if self.max_sm else None,
+                    reasons=sorted(self.reasons), samples=len(self.sm), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 # ----------------------------------------------------------------------------- our arm
+
+def load_traffic(kernel, envs):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken at this size."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        return t[kernel]["dram_bytes_per_launch"] if t.get("envs_per_gpu") == envs else None
+    except Exception:
+        return None
+
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -276,7 +313,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": E * 32 * world, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sf_step_kernel<0>",
+                         "traffic": load_traffic("sf_step_kernel", E), "peak_source": peak_src, "kernel": "sf_step_kernel<0>",
+                         "algo_bytes_per_launch": local_algo / K,
                          "algo_bytes_per_env_step": local_algo / max(1, K * E),
                          "note": "per GPU (rank 0); algorithmic bytes summed on the device from live populations"},
             "clocks": sampler.summary(),
@@ -293,6 +331,7 @@ def run_ours(args):
                 "observe_kernel_ms": ms_obs_only / KO,
                 "roofline": {"bound": "hbm", "kernel": "sf_observe_kernel", "achieved": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9 / peak,
+                             "traffic": load_traffic("sf_observe_kernel", E),
                              "algo_bytes_per_observation": sfcfg.OBS_LEN * 4}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(args.cpu_steps)

@@ -421,6 +421,22 @@ SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
 #endif
     return found;
 }
+/* A player-built cell that nobody stands on carries a HINT of its record's slot in the bits the
+ * occupant does not need (0-7 and 14-15, ten bits).  The hint is always validated against the
+ * record, so a stale one (after a human stood there, or after a swap-remove) only costs the
+ * search; whoever searched writes the fresh hint back. */
+#define C_HINT 0xC0FFu
+SF_FN uint32_t sf_hint_bits(int q) { return ((uint32_t)q & 0xFFu) | (((uint32_t)q >> 8) & 3u) << 14; }
+SF_FN int sf_built_slot(const SfDev &d, int env, const SfEnv &e, int cell, uint32_t g)
+{
+    if (!(g & (C_S0 | C_S1))) {
+        uint32_t hq = (g & 0xFFu) | ((g >> 14) & 3u) << 8;
+        if (hq < e.ntemp && SF_T(d.t_cell, hq) == cell) return (int)hq;
+    }
+    int q = sf_find_built(d, env, e, cell);
+    if (q >= 0 && q < 1024 && !(g & (C_S0 | C_S1))) SF_G(cell) = (uint16_t)((g & ~C_HINT) | sf_hint_bits(q));
+    return q;
+}
 SF_FN void sf_remove_built(const SfDev &d, int env, SfEnv &e, int q)
 {
     uint32_t last = e.ntemp - 1;
@@ -638,22 +654,26 @@ SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 /* destroy test of one player-built cell, second loop of update_tmp, gameplay.hpp:1356-1373 */
 SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, int cell)
 {
-    int q = sf_find_built(d, env, e, cell);
+    uint32_t g = SF_G(cell);
+    int q = sf_built_slot(d, env, e, cell, g);
     if (q >= 0) {
-        uint32_t g = SF_G(cell);
+        g = SF_G(cell);
         uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
         int dmg = SF_T(d.t_dmg, q);
+        /* destroying a record frees the hint bits too (the occupant byte only if nobody is there) */
         if (kind == K_ENTRANCE && !(g & (C_S0 | C_S1)) && dmg >= 1000) { /* lim_portal */
             int pi = SF_T(d.t_pidx, q);
             int ecell = sf_exit_cell(d, k, env, pi);
-            SF_G(ecell) = (uint16_t)(SF_G(ecell) & ~C_KIND);
-            SF_G(cell) = (uint16_t)(g & ~C_KIND);
+            uint32_t ge = SF_G(ecell);
+            SF_G(cell) = (uint16_t)(g & ~(C_KIND | C_HINT));
             m2_clear(e.mp, pi);
             sf_remove_built(d, env, e, q);
-            int q1 = sf_find_built(d, env, e, ecell);
+            int q1 = sf_built_slot(d, env, e, ecell, ge);
+            ge = SF_G(ecell);
+            SF_G(ecell) = (uint16_t)((ge & (C_S0 | C_S1)) ? (ge & ~(C_KIND | 0xC000u)) : (ge & ~(C_KIND | C_HINT)));
             if (q1 >= 0) sf_remove_built(d, env, e, q1);
         } else if (kind == K_BLOCK && dmg >= 1100) { /* lim_block */
-            SF_G(cell) = (uint16_t)(g & ~C_KIND);
+            SF_G(cell) = (uint16_t)(g & ~(C_KIND | C_HINT));
             sf_remove_built(d, env, e, q);
         }
     }
@@ -761,9 +781,9 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
                 const int b = b0 + j;
                 uint32_t kind = (g[j] >> C_KIND_SHIFT) & 7u;
                 if (built_any && (kind == K_BLOCK || (kind == K_ENTRANCE && !(g[j] & (C_S0 | C_S1))))) {
-                    int q = sf_find_built(d, env, e, cell[j]);
+                    int q = sf_built_slot(d, env, e, cell[j], g[j]);
                     SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b);
-                    SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
+                    SF_G(cell[j]) = (uint16_t)(SF_G(cell[j]) & ~C_S2);
                     m2_clear(e.mb, b);
                     if (n_hit == 0) hc0 = cell[j];
                     else if (n_hit == 1) hc1 = cell[j];
@@ -948,19 +968,19 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
             if (c == '[') {
                 if (blocks && sf_push_built(d, k, env, e, nc, 0)) {
-                    SF_G(nc) = (uint16_t)(K_BLOCK << C_KIND_SHIFT);
+                    SF_G(nc) = (uint16_t)((K_BLOCK << C_KIND_SHIFT) | sf_hint_bits((int)e.ntemp - 1));
                     SF_AT(d.h_bp, h) = bp - 1u;
                 }
             } else if (pend) { /* second press: the entrance bound to the pending exit */
                 if (sf_push_built(d, k, env, e, nc, (int)pend - 1)) {
-                    SF_G(nc) = (uint16_t)(K_ENTRANCE << C_KIND_SHIFT);
+                    SF_G(nc) = (uint16_t)((K_ENTRANCE << C_KIND_SHIFT) | sf_hint_bits((int)e.ntemp - 1));
                     SF_AT(d.h_bp, h) = bp & ~0xFF0000u;
                 }
             } else if (portals) { /* first press: the exit, lowest free portal slot (p_ind) */
                 int pi = m2_lowest_free(e.mp);
                 if (pi >= k.cap_p) sf_fail_env(e, SF_OVERFLOW);
                 else if (sf_push_built(d, k, env, e, nc, 0)) {
-                    SF_G(nc) = (uint16_t)(K_EXIT << C_KIND_SHIFT);
+                    SF_G(nc) = (uint16_t)((K_EXIT << C_KIND_SHIFT) | sf_hint_bits((int)e.ntemp - 1));
                     SF_AT(d.p_cell, pi) = (uint16_t)nc;
                     m2_set(e.mp, pi);
                     SF_AT(d.h_bp, h) = (bp - 0x100u) | ((uint32_t)(pi + 1) << 16);

@@ -129,7 +129,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     if (cfg.cap_zombies < 1 || cfg.cap_zombies > SF_LIM_ZOMBIES) return "cap_zombies out of range (1..128)";
     if (cfg.cap_bullets < 1 || cfg.cap_bullets > SF_LIM_BULLETS) return "cap_bullets out of range (1..128)";
     if (cfg.cap_portals < 1 || cfg.cap_portals > SF_LIM_PORTALS) return "cap_portals out of range (1..128)";
-    if (cfg.cap_built < 1 || cfg.cap_built > SF_LIM_BUILT) return "cap_built out of range (1..4096)";
+    if (cfg.cap_built < 1 || cfg.cap_built > SF_LIM_BUILT) return "cap_built out of range (1..1023)";
     if (cfg.cap_chests < 1) return "cap_chests must be positive";
     std::memset(&k, 0, sizeof k);
     k.mode = cfg.mode, k.squad_agents = cfg.squad_agents != 0, k.auto_reset = cfg.auto_reset != 0;

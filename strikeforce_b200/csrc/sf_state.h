@@ -21,6 +21,8 @@
  *              (s[3]+s[10]), 6 player-built entrance (s[5]+s[10]), 7 player-built exit
  *              (s[7]+s[10]).  Chests and built objects both need a '.' cell, so they never
  *              coincide (:536, :706).
+ *   bits 14-15 with bits 0-7: on a player-built cell nobody stands on, a validated hint of the
+ *              slot of its record in the built list (sf_built_slot).
  * The reference's last-writer bullet pointer (node::bullet, trusted only under s[2]) is the
  * BF_OWNS bit of exactly one live bullet standing in that cell ("last writer").
  */
@@ -95,7 +97,7 @@ enum { SH_WALL, SH_HUMAN, SH_ZOMBIE, SH_UP, SH_DOWN, SH_BULLET, SH_CHEST, SH_EXI
 #define SF_LIM_ZOMBIES 128
 #define SF_LIM_BULLETS 128
 #define SF_LIM_PORTALS 128
-#define SF_LIM_BUILT 4096
+#define SF_LIM_BUILT 1023 /* record slots fit the ten hint bits of a cell */
 #define SF_MAX_LEVEL 64
 
 typedef struct SfWpn { int32_t stamina, damage, effect, range; } SfWpn;

@@ -760,15 +760,34 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
     int hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0; /* cells that absorbed a bullet in this call */
     int n_hit = 0;
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
+    /* liveness is tested against a snapshot of the mask (every slot is visited once), and the
+     * flags / positions of a round are loaded one round ahead, so that they are in flight
+     * together with the cell loads of the round before */
+    const uint64_t live0 = e.on ? e.mb[0] : 0ull, live1 = e.on ? e.mb[1] : 0ull;
+    uint32_t meta_n[4], pw_n[4];
+    SF_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        bool ln = j <= hi && (((j < 64 ? live0 : live1) >> (j & 63)) & 1);
+        meta_n[j] = ln ? SF_AT(d.b_meta, j) : 0u;
+        pw_n[j] = ln ? (uint32_t)SF_AT(d.b_pw, j) : 0u;
+    }
     for (int b0 = 0; b0 <= hi; b0 += 4) {
         bool lv[4];
         uint32_t meta[4], g[4];
         int cell[4];
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
-            lv[j] = e.on && b0 + j <= hi && m2_test(e.mb, b0 + j);
-            meta[j] = lv[j] ? SF_AT(d.b_meta, b0 + j) : 0u;
-            cell[j] = lv[j] ? (int)(SF_AT(d.b_pw, b0 + j) & POS_CELL) : 0;
+            const int b = b0 + j;
+            lv[j] = b <= hi && (((b < 64 ? live0 : live1) >> (b & 63)) & 1);
+            meta[j] = meta_n[j];
+            cell[j] = (int)(pw_n[j] & POS_CELL);
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + 4 + j;
+            bool ln = b <= hi && (((b < 64 ? live0 : live1) >> (b & 63)) & 1);
+            meta_n[j] = ln ? SF_AT(d.b_meta, b) : 0u;
+            pw_n[j] = ln ? (uint32_t)SF_AT(d.b_pw, b) : 0u;
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
@@ -845,6 +864,15 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
     SF_SYNCWARP();
     bool oob = false;
     /* reference order: r == 1 ascending, r == 0 descending (:1073-1076); walk the opposite way */
+    const uint64_t live0 = e.on ? e.mb[0] : 0ull, live1 = e.on ? e.mb[1] : 0ull; /* snapshot: each slot is visited once */
+    uint32_t pw_n[4], meta_n[4]; /* loaded one round ahead */
+    SF_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        const int bn = r ? hi - j : j;
+        bool ln = j <= hi && (((bn < 64 ? live0 : live1) >> (bn & 63)) & 1);
+        pw_n[j] = ln ? (uint32_t)SF_AT(d.b_pw, bn) : 0u;
+        meta_n[j] = ln ? SF_AT(d.b_meta, bn) : 0u;
+    }
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
         int b[4], nc[4];
@@ -852,9 +880,16 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
             b[j] = r ? hi - (i0 + j) : i0 + j;
-            lv[j] = e.on && i0 + j <= hi && m2_test(e.mb, b[j]);
-            pw[j] = lv[j] ? SF_AT(d.b_pw, b[j]) : 0u;
-            meta[j] = lv[j] ? (SF_AT(d.b_meta, b[j]) & ~BF_OWNS) : 0u;
+            lv[j] = i0 + j <= hi && (((b[j] < 64 ? live0 : live1) >> (b[j] & 63)) & 1);
+            pw[j] = pw_n[j];
+            meta[j] = meta_n[j] & ~BF_OWNS;
+        }
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int bn = r ? hi - (i0 + 4 + j) : i0 + 4 + j;
+            bool ln = i0 + 4 + j <= hi && (((bn < 64 ? live0 : live1) >> (bn & 63)) & 1);
+            pw_n[j] = ln ? (uint32_t)SF_AT(d.b_pw, bn) : 0u;
+            meta_n[j] = ln ? SF_AT(d.b_meta, bn) : 0u;
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {

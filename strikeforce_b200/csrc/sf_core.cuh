@@ -536,6 +536,15 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
 SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mz) : -1);
+    /* zombies neither appear nor vanish here: liveness comes from a snapshot of the mask, and the
+     * positions of a round are loaded one round ahead */
+    const uint64_t live0 = e.on ? e.mz[0] : 0ull, live1 = e.on ? e.mz[1] : 0ull;
+    uint32_t pw_n[2];
+    SF_UNROLL
+    for (int j = 0; j < 2; ++j) {
+        bool ln = j <= hi && (((j < 64 ? live0 : live1) >> (j & 63)) & 1);
+        pw_n[j] = ln ? (uint32_t)SF_AT(d.z_pos, j) : 0u;
+    }
     for (int z0 = 0; z0 <= hi; z0 += 2) {
         bool act[2];
         uint32_t pw[2];
@@ -543,9 +552,16 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
         uint32_t gv[2][5];
         SF_UNROLL
         for (int j = 0; j < 2; ++j) {
-            act[j] = e.on && z0 + j <= hi && m2_test(e.mz, z0 + j);
-            pw[j] = act[j] ? SF_AT(d.z_pos, z0 + j) : 0u;
+            const int z = z0 + j;
+            act[j] = e.on && z <= hi && (((z < 64 ? live0 : live1) >> (z & 63)) & 1);
+            pw[j] = pw_n[j];
             cell[j] = (int)(pw[j] & POS_CELL);
+        }
+        SF_UNROLL
+        for (int j = 0; j < 2; ++j) {
+            const int z = z0 + 2 + j;
+            bool ln = z <= hi && (((z < 64 ? live0 : live1) >> (z & 63)) & 1);
+            pw_n[j] = ln ? (uint32_t)SF_AT(d.z_pos, z) : 0u;
         }
         SF_UNROLL
         for (int j = 0; j < 2; ++j) {
@@ -977,9 +993,8 @@ SF_FN int sf_key_index(int c, int group)
  * for '[' ']' 'z' 'x', in the walking direction for 'a' 's' 'd' 'w'), and its selection, stamina
  * and mindamage when it fires or consumes -- is loaded up front in one round of independent
  * loads; the rules then run on registers. */
-SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c)
+SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c, uint32_t pw)
 {
-    uint32_t pw = SF_AT(d.h_pw, h);
     int cell = (int)(pw & POS_CELL);
     int way0 = (int)(pw >> POS_HI_SHIFT);
     const bool acts_ahead = c == '[' || c == ']' || c == 'z' || c == 'x';
@@ -1176,9 +1191,22 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     int r = 0;
     if (e.on) r = sf_rand(e, t) & 1;
     SF_SYNCWARP();
+    /* a human's position and command are loaded one iteration ahead (nobody else writes them) */
+    uint32_t pw_n = 0;
+    int c_n = '+';
+    {
+        int h = r ? 0 : hi;
+        if (hi >= 0 && ((live >> h) & 1)) pw_n = SF_AT(d.h_pw, h), c_n = h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h);
+    }
     for (int i = 0; i <= hi; ++i) {
-        int h = r ? i : hi - i;
-        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h));
+        const int h = r ? i : hi - i;
+        const uint32_t pw = pw_n;
+        const int c = c_n;
+        if (i < hi) {
+            int hn = r ? i + 1 : hi - i - 1;
+            if ((live >> hn) & 1) pw_n = SF_AT(d.h_pw, hn), c_n = hn == 0 ? cmd0 : (int)SF_AT(d.h_cmd, hn);
+        }
+        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, c, pw);
         SF_SYNCWARP();
     }
 }

@@ -17,6 +17,8 @@
 
 #include <unistd.h>
 
+#include <sstream>
+
 using namespace Environment::Field;
 namespace ECh = Environment::Character;
 namespace EIt = Environment::Item;
@@ -155,6 +157,70 @@ int sfref_reset(int mode, int level, long long tb, long long serial, const char 
     std::memset(g_hub.captured, 0, sizeof(g_hub.captured));
     track_and_check_caps();
     return 0;
+}
+
+// Replay / logging variants of sfref_reset (reference gameplay.hpp:1749-1794, 966-993): the
+// reference's OWN reader and writer of the .sf_sample format, used to pin strikeforce_b200/replay.py.
+//   replay_path != NULL: load_data() reads seeds, player sheet and later every command from the
+//                        file (the file name is asked on std::cin, so std::cin is redirected);
+//   enable_logging:      load_data() opens ./datasets/.../(date).sf_sample and human_action()
+//                        appends the commands; the seeds are the reference's own (time based),
+//                        read them back with sfref_seeds().
+int sfref_reset_ex(int mode, int level, const char *player_template, int squad_agents, const int *caps,
+                   long max_steps, int enable_logging, const char *replay_path)
+{
+    if (!g_inited) return -1;
+    if (caps) g_caps = Caps{caps[0], caps[1], caps[2], caps[3], caps[4], caps[5]};
+    else g_caps = Caps{9000, 9000, 9000, 9000, 9000, 9000};
+    g_mode = mode;
+    g_template = player_template;
+    g_squad_agents = squad_agents != 0;
+    g_max_steps = max_steps;
+    if (g.log_file.is_open()) g.log_file.close();
+    if (g.replay_file.is_open()) g.replay_file.close();
+    ECh::me = ECh::Human();
+    ECh::me.build(false, "", g_template);
+    g.manual = false;
+    g.replay_mode = replay_path != nullptr;
+    g.enable_logging = enable_logging != 0;
+    g.log_filename = "";
+    g.mode = mode_name(mode);
+    g.level = level;
+    g.chest = 0;
+    std::streambuf *old_cin = std::cin.rdbuf();
+    std::istringstream fake(std::string(replay_path ? replay_path : "") + "\n");
+    std::cin.rdbuf(fake.rdbuf());
+    std::streambuf *old_cout = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf()); // the prompt "Enter the file's address: "
+    g.setup();
+    std::cin.rdbuf(old_cin);
+    std::cout.rdbuf(old_cout);
+    hum[ind].agent->slot = ind;
+    if (g_squad_agents && mode == SF_MODE_SQUAD)
+        for (int i = 1; i < 10; ++i) {
+            g.prepare(hum[i]);
+            hum[i].agent->slot = i;
+        }
+    ++g.frame;
+    g_status = SF_RUNNING;
+    g_steps = 0;
+    g_hw_h = 0;
+    std::memset(g_hub.captured, 0, sizeof(g_hub.captured));
+    track_and_check_caps();
+    return 0;
+}
+
+// the seeds of the running match (after a logging reset: the reference's own, as written to the log)
+void sfref_seeds(long long *out) { out[0] = (long long)g.tb; out[1] = (long long)g.serial_number; }
+
+// close the log of a logging match and return its path (relative to the run directory)
+int sfref_close_log(char *out, int cap)
+{
+    if (g.log_file.is_open()) g.log_file.close();
+    g.enable_logging = false;
+    std::snprintf(out, cap, "%s", g.log_filename.c_str());
+    return (int)g.log_filename.size();
 }
 
 int sfref_status() { return g_status; }

@@ -31,6 +31,10 @@ def lib():
         L.sfref_init.argtypes = [ctypes.c_char_p]
         L.sfref_reset.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong,
                                   ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_long]
+        L.sfref_reset_ex.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_long, ctypes.c_int, ctypes.c_char_p]
+        L.sfref_seeds.argtypes = [ctypes.c_void_p]
+        L.sfref_close_log.argtypes = [ctypes.c_char_p, ctypes.c_int]
         L.sfref_step.argtypes = [ctypes.c_char_p, ctypes.c_int]
         L.sfref_observe.argtypes = [ctypes.c_int, ctypes.c_void_p]
         L.sfref_set_capture.argtypes = [ctypes.c_int, ctypes.c_int]
@@ -77,6 +81,38 @@ def reset(mode, level, tb, serial, template=ACCOUNT1, squad_agents=False, caps=N
                            int(squad_agents), _caps_arr(caps), max_steps)
     if rc != 0:
         raise RuntimeError("sfref_reset failed")
+
+
+def reset_logging(mode, level, template=ACCOUNT1, squad_agents=False, caps=None, max_steps=0):
+    """Start a match with the reference's own .sf_sample logging on (gameplay.hpp:1784-1794, 966-967).
+    The seeds are the reference's (time based): returns (tb, serial)."""
+    L = lib()
+    with _InRundir():
+        rc = L.sfref_reset_ex(mode, level, os.path.abspath(template).encode(), int(squad_agents), _caps_arr(caps),
+                              max_steps, 1, None)
+    if rc != 0:
+        raise RuntimeError("sfref_reset_ex failed")
+    out = np.zeros(2, dtype=np.int64)
+    L.sfref_seeds(out.ctypes.data)
+    return int(out[0]), int(out[1])
+
+
+def close_log():
+    """Close the running log and return its absolute path."""
+    buf = ctypes.create_string_buffer(4096)
+    lib().sfref_close_log(buf, 4096)
+    return os.path.join(RUNDIR, buf.value.decode())
+
+
+def reset_replay(mode, level, path, squad_agents=False, caps=None, max_steps=0):
+    """Start a match that the reference replays from a .sf_sample file with its own reader
+    (gameplay.hpp:1749-1783, 968-993): seeds, player sheet and every command come from the file."""
+    L = lib()
+    with _InRundir():
+        rc = L.sfref_reset_ex(mode, level, os.path.abspath(ACCOUNT1).encode(), int(squad_agents), _caps_arr(caps),
+                              max_steps, 0, os.path.abspath(path).encode())
+    if rc != 0:
+        raise RuntimeError("sfref_reset_ex failed")
 
 
 def step(actions):

@@ -199,3 +199,34 @@ def test_auto_reset_chain_parity(torch_cuda, arena_data):
             assert sim.stats()["episodes"] == sum(episode)
         finally:
             sim.close()
+
+
+def test_replay_of_sf_sample_logs(torch_cuda, arena_data, tmp_path):
+    """.sf_sample logs (strikeforce_b200/replay.py) replayed on the GPU follow the oracle."""
+    import sfo
+    from strikeforce_b200 import replay
+    from strikeforce_b200.sim import BatchedArena
+    rng = np.random.default_rng(21)
+    sheet = arena_data.player_sheet("account1")
+    logs = []
+    for i in range(5):
+        cmds = bytes(sfcfg.ACTIONS28[j] for j in rng.integers(28, size=200))
+        path = tmp_path / ("m%d.sf_sample" % i)
+        replay.write(str(path), 1700000000 + 17 * i, 4242 + i, sheet, cmds, name="p%d" % i)
+        logs.append(replay.read(str(path)))
+    sim = BatchedArena(8, mode="Solo", level=2, auto_reset=False, player=sheet)
+    try:
+        status = replay.drive(sim, logs)
+        h = sim.state_hash().cpu().numpy().view(np.uint64)
+        cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_SOLO, level_min=2, player=sheet)
+        for e, l in enumerate(logs):
+            o = sfo.Arena(cfg)
+            o.reset(2, l.tb, l.serial)
+            for t, c in enumerate(l.commands):
+                st = o.step(bytes([c]))
+                assert status[t, e] == st
+                if st:
+                    break
+            assert h[e] == np.uint64(o.state_hash())
+    finally:
+        sim.close()

@@ -230,3 +230,73 @@ def test_replay_of_sf_sample_logs(torch_cuda, arena_data, tmp_path):
             assert h[e] == np.uint64(o.state_hash())
     finally:
         sim.close()
+
+
+def _sampled_parity(torch, arena_data, n_envs, mode, level_min, level_max, steps, table, sample, player="account1",
+                    squad_agents=False, obs_at=()):
+    """BASELINE.json-size batches: every arena steps on the GPU, a sample of them is followed by the
+    oracle state for state (the whole-batch property: a checksum of all state hashes is finite work
+    for the GPU only; the oracle cannot follow 10^5 arenas)."""
+    from strikeforce_b200.sim import BatchedArena
+    sim = BatchedArena(n_envs, mode=mode, level=level_min, level_max=level_max, squad_agents=squad_agents,
+                       auto_reset=False, player=player)
+    span = level_max - level_min + 1
+    oracles = {}
+    for e in sample:
+        lvl = level_min + e % span
+        cfg = sfcfg.make_config(arena_data, mode=mode, level_min=lvl, squad_agents=squad_agents, player=player)
+        o = sfo.Arena(cfg)
+        o.reset(lvl, common.synth_tb(e), common.synth_serial(e, 0))
+        oracles[e] = o
+    idx = torch.tensor(sample, device=sim.device)
+    try:
+        for t in range(steps):
+            if t in obs_at:
+                obs = sim.observe(1)
+                picked = obs[idx].reshape(len(sample), -1).cpu().numpy()
+                del obs
+                for i, e in enumerate(sample):
+                    assert (picked[i].view(np.uint32) == oracles[e].observe(0).view(np.uint32)).all(), \
+                        "observation differs: env %d step %d" % (e, t)
+            act = sim.synth_actions(t, table)
+            sim.step(act)
+            h = sim.state_hash()[idx].cpu().numpy().view(np.uint64)
+            st = sim.step_out()[idx, 0].cpu().numpy()
+            ref_act = common.synth_actions(sample, sim.n_agents, t, table)
+            for i, e in enumerate(sample):
+                s = oracles[e].step(bytes(ref_act[i]))
+                assert st[i] == s, "status differs: env %d step %d" % (e, t)
+                if s in (sfcfg.RUNNING, sfcfg.DEAD, sfcfg.WIN, sfcfg.TIMEOUT):
+                    assert h[i] == np.uint64(oracles[e].state_hash()), "state differs: env %d step %d" % (e, t)
+        stats = sim.stats()
+        assert stats["steps"] + stats["overflows"] + stats["ub_guards"] >= n_envs * steps - stats["episodes"] * steps
+        return stats
+    finally:
+        sim.close()
+
+
+import sfo  # noqa: E402  (oracle binding; test infrastructure)
+
+
+def test_config2_solo_4096_every_arena(torch_cuda, arena_data):
+    """BASELINE.json configs[1]: Solo, 4,096 arenas on one GPU, random 9-symbol actions; EVERY arena
+    is compared with the CPU oracle after every step."""
+    _sampled_parity(torch_cuda, arena_data, 4096, sfcfg.MODE_SOLO, 1, 1, 40, sfcfg.ACTIONS9, list(range(4096)),
+                    obs_at=(39,))
+
+
+def test_config3_timer_65536_sampled(torch_cuda, arena_data):
+    """configs[2]: Timer mode, 65,536 arenas, consumables / throwables sheet, levels 1-10, 28-symbol
+    alphabet, observation tensors emitted on the device; 192 sampled arenas followed by the oracle."""
+    rng = np.random.default_rng(3)
+    sample = sorted(set(rng.integers(0, 65536, size=190).tolist()) | {0, 65535})
+    _sampled_parity(torch_cuda, arena_data, 65536, sfcfg.MODE_TIMER, 1, 10, 120, sfcfg.ACTIONS28, sample,
+                    player="synthetic", obs_at=(0, 119))
+
+
+def test_config4_squad_shard_131072_sampled(torch_cuda, arena_data):
+    """configs[3]: one GPU's shard (131,072 arenas) of the Squad 5v5 batch, blocks and portals in the
+    alphabet, levels 1-10; 160 sampled arenas followed by the oracle."""
+    rng = np.random.default_rng(4)
+    sample = sorted(set(rng.integers(0, 131072, size=158).tolist()) | {0, 131071})
+    _sampled_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 100, sfcfg.ACTIONS28, sample)

@@ -93,9 +93,12 @@ class Arena:
             raise RuntimeError("sfo_create failed (caps too large for the model?)")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().sfo_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) and _lib is not None:
+                _lib.sfo_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass  # interpreter shutdown
 
     def reset(self, level, tb, serial):
         lib().sfo_reset(self._h, level, tb, serial)

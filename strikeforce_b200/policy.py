@@ -1,0 +1,143 @@
+"""Batched twin of the reference's policy network.
+
+``AgentModel`` of ``bots/bot-0.5/Modules.hpp`` (lines 29-180) -- a 4-layer stride-2 CNN
+(31 -> 15 -> 7 -> 3 -> 1, no bias), two single-layer GRUs, a 5-cell "point of view" gather, a
+linear mixer and two residual heads -- evaluates ONE observation per call and keeps the GRU state
+and the last action inside the module (``reset_memory`` / ``update_actions``).  Here the same
+arithmetic runs on a batch ``[B, 32, 31, 31]`` that never leaves the device, with the recurrent
+state as explicit ``[B, 160]`` tensors; every "divide by the mean absolute value" of the
+reference (a reduction over the whole tensor of its single sample) is a per-sample reduction.
+The layers are library calls (cuDNN / cuBLAS through torch), exactly as the reference's are
+libtorch calls; parameter names and shapes match the reference's ``named_parameters()`` so that a
+``model.pt`` state can be exchanged.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _l1norm(x, size):
+    """x * size / (sum |x| + 1e-8) per sample (Modules.hpp:45, 109, 113, ...)."""
+    flat = x.reshape(x.shape[0], -1)
+    return x * (size / (flat.abs().sum(dim=1) + 1e-8)).view(-1, *([1] * (x.dim() - 1)))
+
+
+class ResB(nn.Module):
+    """Modules.hpp:29-52"""
+
+    def __init__(self, hidden, layers):
+        super().__init__()
+        for i in range(layers):
+            setattr(self, "lin%d" % i, nn.Linear(hidden, hidden))
+        self.n = layers
+
+    def forward(self, x):
+        x = _l1norm(x, x[0].numel())
+        for i in range(self.n):
+            y = F.relu(getattr(self, "lin%d" % i)(x)) + x
+            x = _l1norm(y, y[0].numel())
+        return x
+
+
+class GameCNN(nn.Module):
+    """Modules.hpp:54-74"""
+
+    def __init__(self, channels, d_out, layers):
+        super().__init__()
+        for i in range(layers):
+            setattr(self, "conv%d" % i, nn.Conv2d(channels if i == 0 else d_out, d_out, 3, stride=2, padding=0, bias=False))
+        self.n = layers
+
+    def forward(self, x):
+        for i in range(self.n):
+            x = getattr(self, "conv%d" % i)(x)
+        return x
+
+
+class Backbone(nn.Module):
+    """Modules.hpp:76-136; the recurrent state is passed in and returned instead of being kept."""
+
+    def __init__(self, channels=32, grid=31, hidden=160, actions=9):
+        super().__init__()
+        self.channels, self.grid, self.hidden, self.actions = channels, grid, hidden, actions
+        self.cnn = GameCNN(channels, hidden, 4)
+        self.gru0 = nn.GRU(hidden, hidden, num_layers=1)
+        self.combined_processor = nn.Sequential(nn.Linear(2 * hidden + actions, hidden))
+        self.gru1 = nn.GRU(hidden, hidden, num_layers=1)
+
+    def initial_state(self, batch, device=None):
+        """reset_memory(), Modules.hpp:94-99: zero GRU states and the action one-hot on index 0."""
+        a = torch.zeros(batch, self.actions, device=device)
+        a[:, 0] = 1
+        return torch.zeros(batch, self.hidden, device=device), torch.zeros(batch, self.hidden, device=device), a
+
+    def forward(self, x, h0, h1, action_input):
+        B, H = x.shape[0], self.hidden
+        feat = _l1norm(self.cnn(x), H)                      # [B, H, 1, 1]
+        out0, h0n = self.gru0(feat.view(1, B, H), h0.view(1, B, H))
+        out_seq = _l1norm(out0.view(B, H), H)
+        c = self.grid // 2                                   # the five cells around the agent, :115-121
+        cells = [(-1, 0), (0, -1), (0, 0), (0, 1), (1, 0)]
+        pov = torch.cat([x[:, :, c + dr, c + dc] for dr, dc in cells] + [action_input], dim=1)
+        combined = torch.cat([out_seq + feat.view(B, H), _l1norm(pov, H)], dim=1)
+        gated = _l1norm(self.combined_processor(combined), H)
+        out1, h1n = self.gru1(gated.view(1, B, H), h1.view(1, B, H))
+        out = _l1norm(out1.view(B, H), H) + gated
+        return out, h0n.view(B, H), h1n.view(B, H)
+
+
+class AgentModel(nn.Module):
+    """Modules.hpp:138-180: ``forward`` returns (p [B, 9], v [B], new state)."""
+
+    def __init__(self, channels=32, grid=31, hidden=160, actions=9, head_layers=3):
+        super().__init__()
+        self.backbone = Backbone(channels, grid, hidden, actions)
+        self.value = nn.Sequential(ResB(hidden, head_layers), nn.Linear(hidden, 1))
+        self.policy = nn.Sequential(ResB(hidden, head_layers), nn.Linear(hidden, actions))
+
+    def initial_state(self, batch, device=None):
+        return self.backbone.initial_state(batch, device)
+
+    def forward(self, x, state):
+        h0, h1, a = state
+        gated, h0, h1 = self.backbone(x, h0, h1, a)
+        p = torch.softmax(self.policy(gated), dim=-1) + 1e-8
+        v = torch.sigmoid(self.value(gated)).view(-1)
+        return p, v, (h0, h1, a)
+
+    @staticmethod
+    def with_action(state, actions):
+        """update_actions(one_hot), Modules.hpp:101-103: the chosen action is fed back next call."""
+        h0, h1, a = state
+        return h0, h1, F.one_hot(actions, a.shape[1]).to(a.dtype)
+
+
+class PolicyAgent:
+    """``Agent`` of bots/bot-0.5/Agent.hpp:178-224 for a batch: ``predict`` runs the network on the
+    observations of ``sf_observe`` and samples an action per row with a seeded device generator
+    (the reference samples with std::random_device, which cannot be reproduced)."""
+
+    def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False):
+        self.model = model.to(device).eval()
+        self.state = model.initial_state(batch, device)
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self.training = training
+
+    @torch.no_grad()
+    def predict(self, obs):
+        p, _, st = self.model(obs, self.state)
+        act = torch.multinomial(p, 1, generator=self.gen).view(-1)
+        self.state = AgentModel.with_action(st, act)
+        return act
+
+    def update(self, actions, imitate):
+        return None
+
+    def in_training(self):
+        return self.training
+
+    def is_manual(self):
+        return False

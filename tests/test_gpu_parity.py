@@ -300,3 +300,34 @@ def test_config4_squad_shard_131072_sampled(torch_cuda, arena_data):
     rng = np.random.default_rng(4)
     sample = sorted(set(rng.integers(0, 131072, size=158).tolist()) | {0, 131071})
     _sampled_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 100, sfcfg.ACTIONS28, sample)
+
+
+def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):
+    """observe -> batched AgentModel forward -> sampled commands -> step, as gameplay::play() does
+    with a bot (gameplay.hpp:956, 933), for the player and for agent-driven squad humans (P2)."""
+    from strikeforce_b200 import bots, policy
+    from strikeforce_b200.sim import BatchedArena
+    torch = torch_cuda
+    torch.manual_seed(0)
+    for agents in (False, True):
+        sim = BatchedArena(96, mode="Squad", level=2, squad_agents=agents, auto_reset=True, max_steps=30)
+        try:
+            rows = 96 * (9 if agents else 1)  # the largest batch a predict() call sees
+            model = policy.AgentModel()
+
+            class TwoAgents(bots.Custom):  # the player and the squad humans keep separate recurrent states
+                def __init__(self):
+                    super().__init__()
+                    self.p1 = policy.PolicyAgent(model, 96, device=sim.device, seed=1)
+                    self.p2 = policy.PolicyAgent(model, rows, device=sim.device, seed=2)
+
+                def bot(self, s, agent_mask=1, phase=sfcfg.OBS_P1):
+                    self.agent = self.p1 if phase == sfcfg.OBS_P1 else self.p2
+                    return super().bot(s, agent_mask, phase)
+
+            c = TwoAgents()
+            c.agent = c.p1
+            stats = bots.play(sim, c, 12)
+            assert stats["steps"] + stats["overflows"] + stats["ub_guards"] == 96 * 12
+        finally:
+            sim.close()

@@ -1,0 +1,90 @@
+"""the batched policy network (strikeforce_b200/policy.py) against outputs of the
+reference's OWN AgentModel (bots/bot-0.5/Modules.hpp, run with libtorch by
+oracle/ref_harness/policy_oracle.cpp; fixture tests/golden/policy_golden.bin).  Parameters and
+observations come from a closed integer-hash formula on both sides, so the fixture holds only the
+network's outputs.  Tolerance 2e-6 absolute on probabilities / values (fp32 reductions in a
+different order: batched rows instead of single-sample tensors)."""
+import os
+import struct
+
+import numpy as np
+import torch
+
+from strikeforce_b200.policy import AgentModel, PolicyAgent
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_golden.bin")
+TOL = 2e-6
+
+
+def hash_unit(i, k):
+    u = (i.astype(np.uint64) * 2654435761 + k * 40503 + 12345) & 0xFFFFFFFF
+    u ^= u >> 15
+    u = (u * 2246822519) & 0xFFFFFFFF
+    u ^= u >> 13
+    return ((u >> 8).astype(np.float32) / np.float32(16777216.0)).astype(np.float32)
+
+
+def read_golden():
+    out, pos = {}, 0
+    data = open(GOLDEN, "rb").read()
+    while pos < len(data):
+        n = struct.unpack_from("<i", data, pos)[0]
+        name = data[pos + 4:pos + 4 + n].decode()
+        pos += 4 + n
+        nd = struct.unpack_from("<i", data, pos)[0]
+        shape = struct.unpack_from("<%dq" % nd, data, pos + 4)
+        pos += 4 + 8 * nd
+        cnt = int(np.prod(shape)) if nd else 1
+        out[name] = np.frombuffer(data, dtype=np.float32, count=cnt, offset=pos).reshape(shape).copy()
+        pos += 4 * cnt
+    return out
+
+
+def formula_model():
+    m = AgentModel()
+    with torch.no_grad():
+        for k, (_, p) in enumerate(m.named_parameters()):  # same registration order as the reference
+            i = np.arange(p.numel(), dtype=np.uint64)
+            w = ((hash_unit(i, k) - np.float32(0.5)) * np.float32(0.16)).astype(np.float32)
+            p.copy_(torch.from_numpy(w).view(p.shape))
+    return m.eval()
+
+
+def formula_obs(s):
+    i = np.arange(32 * 31 * 31, dtype=np.uint64)
+    x = np.where(hash_unit(i, 1000 + s) < np.float32(0.08), hash_unit(i, 2000 + s) * np.float32(1.5), np.float32(0))
+    return torch.from_numpy(x.astype(np.float32)).view(1, 32, 31, 31)
+
+
+def test_parameter_names_match_the_reference():
+    names = [n for n, _ in AgentModel().named_parameters()]
+    assert names[:4] == ["backbone.cnn.conv0.weight", "backbone.cnn.conv1.weight", "backbone.cnn.conv2.weight",
+                         "backbone.cnn.conv3.weight"]
+    assert "backbone.combined_processor.0.weight" in names and "policy.1.bias" in names and len(names) == 30
+
+
+def test_batched_forward_matches_the_reference_network():
+    g = read_golden()
+    steps = len([k for k in g if k.startswith("p:")])
+    m = formula_model()
+    # the golden sequence is row 1 of a batch of three; rows 0 and 2 see other inputs
+    B = 3
+    st = m.initial_state(B)
+    with torch.no_grad():
+        for s in range(steps):
+            x = torch.cat([formula_obs(s + 7), formula_obs(s), formula_obs(s + 13)])
+            p, v, st = m(x, st)
+            assert np.abs(p[1].numpy() - g["p:%d" % s]).max() < TOL, "policy, step %d" % s
+            assert np.abs(v[1].numpy() - g["v:%d" % s]).max() < TOL, "value, step %d" % s
+            assert abs(float(p[1].sum()) - 1.0) < 1e-5
+            act = torch.tensor([(s + 2) % 9, (s * 4 + 1) % 9, (s + 5) % 9])  # row 1: the action the oracle fed back
+            st = AgentModel.with_action(st, act)
+
+
+def test_policy_agent_is_seeded_and_batched():
+    m = formula_model()
+    a1, a2 = PolicyAgent(m, 4, device="cpu", seed=3), PolicyAgent(m, 4, device="cpu", seed=3)
+    x = torch.cat([formula_obs(s) for s in range(4)])
+    for _ in range(3):
+        r1, r2 = a1.predict(x), a2.predict(x)
+        assert r1.shape == (4,) and torch.equal(r1, r2) and int(r1.max()) < 9

@@ -993,7 +993,8 @@ SF_FN int sf_key_index(int c, int group)
  * for '[' ']' 'z' 'x', in the walking direction for 'a' 's' 'd' 'w'), and its selection, stamina
  * and mindamage when it fires or consumes -- is loaded up front in one round of independent
  * loads; the rules then run on registers. */
-SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c, uint32_t pw)
+SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e, int h, int c, uint32_t pw,
+                   uint32_t sel)
 {
     int cell = (int)(pw & POS_CELL);
     int way0 = (int)(pw >> POS_HI_SHIFT);
@@ -1003,9 +1004,11 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
     int nc = cell;
     const bool inb = (acts_ahead || walks) && sf_neighbour(cell, dir, &nc);
     const bool uses_kit = c == 'x' || c == 'z' || c == 'u';
-    uint32_t g = SF_G(cell);
+    /* the human's own cell matters only if it leaves it, or waits on a player-built entrance
+       (HS_ON_ENT); a human that stays put stands on nothing it could claim or enter */
+    bool have_g = walks || (sel & HS_ON_ENT);
+    uint32_t g = have_g ? (uint32_t)SF_G(cell) : 0u;
     uint32_t gn = inb ? (uint32_t)SF_G(nc) : 0u;
-    uint32_t sel = uses_kit ? (uint32_t)SF_AT(d.h_sel, h) : 0u;
     int st = uses_kit ? SF_AT(d.h_stam, h) : 0;
     int md = uses_kit ? SF_AT(d.h_mind, h) : 0;
     const int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
@@ -1061,7 +1064,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                 SF_AT(d.h_hp, h) += k.cons[ind].hp;
                 SF_AT(d.h_mind, h) = md + k.cons[ind].effect;
                 SF_AT(d.h_cons, h) = cp - (1u << (8 * ind));
-                if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT)); /* vec = -1 */
+                if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel &= ~(3u << HS_VEC_SHIFT)); /* vec = -1 */
             }
         }
     } else if (c == 'z' || c == 'x') {
@@ -1081,11 +1084,11 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                     uint32_t tp = SF_AT(d.h_thr, h);
                     uint32_t cnt = (tp >> (8 * ind)) & 0xFFu;
                     if (cnt < 1) {
-                        SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT));
+                        SF_AT(d.h_sel, h) = (uint16_t)(sel &= ~(3u << HS_VEC_SHIFT));
                     } else {
                         SF_AT(d.h_stam, h) = st + w.stamina;
                         SF_AT(d.h_thr, h) = tp - (1u << (8 * ind));
-                        if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel & ~(3u << HS_VEC_SHIFT));
+                        if (cnt - 1 < 1) SF_AT(d.h_sel, h) = (uint16_t)(sel &= ~(3u << HS_VEC_SHIFT));
                         can = true;
                     }
                 }
@@ -1116,18 +1119,18 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         int i;
         if ((i = sf_key_index(c, 0)) >= 0) {
             if ((SF_AT(d.h_cons, h) >> (8 * i)) & 0xFFu) {
-                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (1u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = sel & HS_KEEP;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel = s4 | (1u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         } else if ((i = sf_key_index(c, 1)) >= 0) {
             if ((SF_AT(d.h_thr, h) >> (8 * i)) & 0xFFu) {
-                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (2u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = sel & HS_KEEP;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel = s4 | (2u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         } else if ((i = sf_key_index(c, 2)) >= 0) {
             if ((sf_tmpl(k, h).w_owned >> i) & 1u) {
-                uint32_t s4 = SF_AT(d.h_sel, h) & 0xFu;
-                SF_AT(d.h_sel, h) = (uint16_t)(s4 | (3u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
+                uint32_t s4 = sel & HS_KEEP;
+                SF_AT(d.h_sel, h) = (uint16_t)(sel = s4 | (3u << HS_VEC_SHIFT) | ((uint32_t)(i + 1) << HS_IND_SHIFT));
             }
         }
     }
@@ -1141,6 +1144,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             int dc = sf_exit_cell(d, k, env, pidx);
             uint32_t gd = SF_G(dc);
             if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
+                if (!have_g) g = SF_G(cell), have_g = true;
                 gd = (gd & ~C_OCC) | C_S0 | (uint32_t)h;
                 SF_G(dc) = (uint16_t)gd;
                 SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
@@ -1158,6 +1162,10 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             SF_AT(d.h_mind, h) += k.cons[ty].effect;
             SF_G(cell) = (uint16_t)(g & ~C_KIND);
             e.chest -= 1;
+        }
+        if (have_g) { /* still on a player-built entrance: its exit was taken, try again next step */
+            const uint32_t ent = kind == K_ENTRANCE ? HS_ON_ENT : 0u;
+            if (ent != (sel & HS_ON_ENT)) SF_AT(d.h_sel, h) = (uint16_t)(sel ^ HS_ON_ENT);
         }
     }
 }
@@ -1192,21 +1200,23 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     if (e.on) r = sf_rand(e, t) & 1;
     SF_SYNCWARP();
     /* a human's position and command are loaded one iteration ahead (nobody else writes them) */
-    uint32_t pw_n = 0;
+    uint32_t pw_n = 0, sel_n = 0;
     int c_n = '+';
     {
         int h = r ? 0 : hi;
-        if (hi >= 0 && ((live >> h) & 1)) pw_n = SF_AT(d.h_pw, h), c_n = h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h);
+        if (hi >= 0 && ((live >> h) & 1))
+            pw_n = SF_AT(d.h_pw, h), sel_n = SF_AT(d.h_sel, h), c_n = h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h);
     }
     for (int i = 0; i <= hi; ++i) {
         const int h = r ? i : hi - i;
-        const uint32_t pw = pw_n;
+        const uint32_t pw = pw_n, sel = sel_n;
         const int c = c_n;
         if (i < hi) {
             int hn = r ? i + 1 : hi - i - 1;
-            if ((live >> hn) & 1) pw_n = SF_AT(d.h_pw, hn), c_n = hn == 0 ? cmd0 : (int)SF_AT(d.h_cmd, hn);
+            if ((live >> hn) & 1)
+                pw_n = SF_AT(d.h_pw, hn), sel_n = SF_AT(d.h_sel, hn), c_n = hn == 0 ? cmd0 : (int)SF_AT(d.h_cmd, hn);
         }
-        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, c, pw);
+        if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, c, pw, sel);
         SF_SYNCWARP();
     }
 }

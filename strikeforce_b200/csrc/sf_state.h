@@ -80,12 +80,14 @@ enum { K_NONE = 0, K_CHEST0 = 1, K_BLOCK = 5, K_ENTRANCE = 6, K_EXIT = 7 };
 /* what node::showit() prints (gameplay.hpp:321-341) */
 enum { SH_WALL, SH_HUMAN, SH_ZOMBIE, SH_UP, SH_DOWN, SH_BULLET, SH_CHEST, SH_EXIT, SH_DOT };
 
-/* human word h_sel: team | rnpc | agent | vec+1 | ind+1 */
+/* human word h_sel: team | rnpc | agent | vec+1 | ind+1 | on-entrance */
 #define HS_TEAM 0x0003u
 #define HS_RNPC 0x0004u
 #define HS_AGENT 0x0008u
 #define HS_VEC_SHIFT 4 /* 2 bits, stores vec + 1 */
 #define HS_IND_SHIFT 6 /* 4 bits, stores ind + 1 */
+#define HS_ON_ENT 0x0400u /* stands on a player-built entrance whose exit was taken (sf_obey) */
+#define HS_KEEP (0x000Fu | HS_ON_ENT) /* what a new selection leaves alone */
 /* position words: cell id in bits 0-13, (way - 1) or `super` in bits 14-15 */
 #define POS_CELL 0x3FFFu
 #define POS_HI_SHIFT 14

@@ -64,6 +64,7 @@ struct SfEnv {
     uint32_t W;          /* sum of the values random[10..17] (see sf_rand) */
     bool fast;           /* both seeds below 10^10: terms 10..17 are the plain window W */
     bool bank;           /* which half of rng_cst holds this stream's term constants */
+    bool watch;          /* something may stand on a portal exit (sf_portal_damage); false = provably nothing */
 };
 
 /* ------------------------------------------------------------------ small helpers */
@@ -182,6 +183,12 @@ SF_FN int sf_showit(uint32_t st, uint32_t g)
     if (kind >= K_CHEST0 && kind < K_BLOCK) return SH_CHEST;
     if ((st & M_EXIT) || kind == K_EXIT) return SH_EXIT;
     return SH_DOT;
+}
+
+/* a portal exit, static ('O' of the map) or player-built */
+SF_FN bool sf_is_exit(const SfTabs &t, int cell, uint32_t g)
+{
+    return (t.smap[cell] & M_EXIT) || ((g >> C_KIND_SHIFT) & 7u) == K_EXIT;
 }
 
 /* ------------------------------------------------------------------ random.hpp */
@@ -591,6 +598,7 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                                 int nc = sf_step_cell(cell[j], i1);
                                 int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
                                 sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
+                                if (sf_is_exit(t, nc, gn)) e.watch = true;
                                 if (j == 0) { /* forward the new s[2] to the second zombie's copy */
                                     if (cell[1] == nc) gv[1][0] = gn | C_S2;
                                     SF_UNROLL
@@ -644,27 +652,36 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
  * forwarding. */
 SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
-    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mp) : -1);
+    /* e.watch: whoever puts a human or a bullet on an exit cell raises it (zombies never enter
+     * one); an arena whose flag is down reads none of its exits, and the flag comes down again
+     * when a pass finds every exit free */
+    const bool look = e.on && e.watch;
+    const int hi = SF_WARP_MAX(look ? m2_highest(e.mp) : -1);
+    bool any = false;
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
         int cell[4];
         uint32_t g[4];
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
-            lv[j] = e.on && i0 + j <= hi && m2_test(e.mp, i0 + j);
+            lv[j] = look && i0 + j <= hi && m2_test(e.mp, i0 + j);
             cell[j] = lv[j] ? sf_exit_cell(d, k, env, i0 + j) : 0;
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
-            if (lv[j] && e.on && (g[j] & (C_S0 | C_S1 | C_S2))) {
-                int b = sf_alloc_bullet(k, e);
-                if (b >= 0) sf_place_bullet(d, env, e, b, cell[j], g[j], 2, 1, -1, 20, -10);
+            if (lv[j] && (g[j] & (C_S0 | C_S1 | C_S2))) {
+                any = true;
+                if (e.on) {
+                    int b = sf_alloc_bullet(k, e);
+                    if (b >= 0) sf_place_bullet(d, env, e, b, cell[j], g[j], 2, 1, -1, 20, -10);
+                }
             }
         }
         SF_SYNCWARP();
     }
+    if (look) e.watch = any;
 }
 
 /* destroy test of one player-built cell, second loop of update_tmp, gameplay.hpp:1356-1373 */
@@ -930,6 +947,7 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
                     uint32_t m = meta[j];
                     if (!(gn[j] & C_S2)) m |= BF_OWNS;
                     SF_G(nc[j]) = (uint16_t)(gn[j] | C_S2);
+                    if (sf_is_exit(t, nc[j], gn[j])) e.watch = true;
                     SF_AT(d.b_pw, b[j]) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc[j]);
                     SF_AT(d.b_meta, b[j]) = m + 0x100u;
                     SF_UNROLL
@@ -1049,6 +1067,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             if (sit == SH_CHEST || sit == SH_UP || sit == SH_DOWN || sit == SH_DOT || sit == SH_BULLET) {
                 gn = (gn & ~C_OCC) | C_S0 | (uint32_t)h;
                 SF_G(nc) = (uint16_t)gn;
+                if (sf_is_exit(t, nc, gn)) e.watch = true; /* an exit under a bullet prints '*' */
                 SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
                 cell = nc;
                 g = gn;
@@ -1111,6 +1130,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                     else {
                         m2_set(e.mb, b);
                         sf_place_bullet(d, env, e, b, nc, gn, way0, range, h, dmg, eff);
+                        if (sf_is_exit(t, nc, gn)) e.watch = true;
                     }
                 }
             }
@@ -1146,6 +1166,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
             if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
                 if (!have_g) g = SF_G(cell), have_g = true;
                 gd = (gd & ~C_OCC) | C_S0 | (uint32_t)h;
+                e.watch = true;
                 SF_G(dc) = (uint16_t)gd;
                 SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
                 cell = dc;
@@ -1248,6 +1269,7 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
     e.ntemp = 0;
     e.status = SF_RUNNING;
     e.on = true;
+    e.watch = true; /* until the first look */
     e.quit = 0;
     e.mz[0] = e.mz[1] = e.mb[0] = e.mb[1] = 0;
     e.mp[0] = (1ull << k.n_static_exits) - 1ull;
@@ -1346,6 +1368,7 @@ SF_FN void sf_load_env(const SfDev &d, int env, SfEnv &e)
     e.env = env;
     e.fast = (misc >> 24) & 1u;
     e.bank = (misc >> 25) & 1u;
+    e.watch = (misc >> 26) & 1u;
     SF_UNROLL
     for (int j = 0; j < 9; ++j) e.Lp[j] = SF_AT(d.rng_log, j);
     SF_UNROLL
@@ -1360,7 +1383,7 @@ SF_FN void sf_store_env(const SfDev &d, int env, const SfEnv &e)
     d.frame[env] = e.frame;
     d.kills[env] = e.kills, d.tkills[env] = e.tkills, d.loot[env] = e.loot, d.chest[env] = e.chest;
     d.misc[env] = (uint32_t)e.level | ((uint32_t)e.status << 8) | ((uint32_t)e.hw_h << 16) | (e.fast ? 1u << 24 : 0u) |
-                  (e.bank ? 1u << 25 : 0u);
+                  (e.bank ? 1u << 25 : 0u) | (e.watch ? 1u << 26 : 0u);
     d.steps[env] = e.steps, d.episode[env] = e.episode, d.ntemp[env] = e.ntemp;
     d.mh[env] = e.mh;
     SF_AT(d.mz, 0) = e.mz[0], SF_AT(d.mz, 1) = e.mz[1];
@@ -1446,6 +1469,7 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         o.status = e.status;
         o.episode_steps = (int32_t)e.steps;
         d.out[env] = o;
+        if (d.out_mirror) d.out_mirror[env] = o; /* straight into the caller's host buffer, no copy afterwards */
     }
     bool reset = false;
     if (was_on) {

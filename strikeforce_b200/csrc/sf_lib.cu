@@ -575,9 +575,20 @@ int sf_step_host(sf_handle *h, const uint8_t *actions_host, sf_step_out *out_hos
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     size_t na = (size_t)h->d.n_envs * (size_t)h->k.n_agents;
     SF_CUDA(h, cudaMemcpyAsync(h->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
+    /* a pinned (cudaHostAlloc / cudaHostRegister) result buffer is written by the kernel itself as
+       each warp finishes its arenas, so the transfer overlaps the step; a pageable one gets a copy */
+    sf_step_out *mirror = nullptr;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+        mirror = static_cast<sf_step_out *>(pa.devicePointer);
+    else
+        cudaGetLastError();
+    h->d.out_mirror = mirror;
     int rc = sf_launch_step(h, SF_HALF_BOTH, h->d_actions, s);
+    h->d.out_mirror = nullptr;
     if (rc) return rc;
-    SF_CUDA(h, cudaMemcpyAsync(out_host, h->d.out, (size_t)h->d.n_envs * sizeof(sf_step_out), cudaMemcpyDeviceToHost, s));
+    if (!mirror)
+        SF_CUDA(h, cudaMemcpyAsync(out_host, h->d.out, (size_t)h->d.n_envs * sizeof(sf_step_out), cudaMemcpyDeviceToHost, s));
     SF_CUDA(h, cudaStreamSynchronize(s));
     return SF_OK;
 }

@@ -137,7 +137,7 @@ typedef struct SfDev {
     /* header */
     uint32_t *frame;
     int32_t *kills, *tkills, *loot, *chest;
-    uint32_t *misc;    /* level | status << 8 | hw_h << 16 | fast-seed flag << 24 | rng_cst bank << 25 */
+    uint32_t *misc;    /* level | status << 8 | hw_h << 16 | fast-seed flag << 24 | rng_cst bank << 25 | exit watch << 26 */
     uint32_t *steps, *episode, *ntemp;
     uint64_t *mh, *mz, *mb, *mp; /* live masks: mh[E], mz[2][E], mb[2][E], mp[2][E] */
     /* random.hpp state in the discrete-log domain */
@@ -171,6 +171,7 @@ typedef struct SfDev {
     uint16_t *grid;
     /* per-step results and running statistics */
     sf_step_out *out;
+    sf_step_out *out_mirror; /* sf_step_host: the caller's pinned host buffer as the device sees it, or NULL */
     unsigned long long *stats; /* [SF_STAT_COUNT] */
     /* shared tables in global memory */
     const uint8_t *smap;      /* [SF_TCELLS] static map bytes, tiled like the overlay */

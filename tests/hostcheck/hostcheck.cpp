@@ -125,6 +125,7 @@ unsigned long long hc_hash(HcHandle *h, int env)
 
 void hc_step_out(HcHandle *h, int env, sf_step_out *out) { *out = h->d.out[env]; }
 int hc_status(HcHandle *h, int env) { return (int)((h->d.misc[env] >> 8) & 0xFF); }
+unsigned hc_misc(HcHandle *h, int env) { return h->d.misc[env]; }
 void hc_stats(HcHandle *h, unsigned long long *out)
 {
     for (int i = 0; i < SF_STAT_COUNT; ++i) out[i] = h->stats[i];

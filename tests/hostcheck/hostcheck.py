@@ -45,6 +45,8 @@ def lib():
         L.hc_hash.restype = C.c_ulonglong
         L.hc_step_out.argtypes = [C.c_void_p, C.c_int, C.POINTER(sfcfg.StepOut)]
         L.hc_status.argtypes = [C.c_void_p, C.c_int]
+        L.hc_misc.argtypes = [C.c_void_p, C.c_int]
+        L.hc_misc.restype = C.c_uint
         L.hc_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.hc_observe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.hc_n_agents.argtypes = [C.c_void_p]
@@ -89,6 +91,10 @@ class HostSim:
 
     def status(self, env):
         return lib().hc_status(self._h, env)
+
+    def misc(self, env):
+        """the packed header word (sf_state.h SfDev::misc)"""
+        return lib().hc_misc(self._h, env)
 
     def step_out(self, env):
         o = sfcfg.StepOut()

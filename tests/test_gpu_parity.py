@@ -120,12 +120,20 @@ def test_overflow_and_truncation_status(torch_cuda, arena_data):
     _run_parity(torch_cuda, arena_data, sfcfg.MODE_SOLO, 1, 32, 400, sfcfg.ACTIONS28, caps=caps, max_steps=300)
 
 
-def test_step_host_matches_device_step(torch_cuda, arena_data):
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_step_host_matches_device_step(torch_cuda, arena_data, pinned):
+    """sf_step_host with a pageable result buffer (copied after the step) and a page-locked one
+    (written by the kernel itself)."""
+    import torch
     from strikeforce_b200.sim import BatchedArena
     a = BatchedArena(64, mode="Solo", auto_reset=True, max_steps=50)
     b = BatchedArena(64, mode="Solo", auto_reset=True, max_steps=50)
     try:
-        out_h = np.zeros(64, dtype=sfcfg.STEP_OUT_DTYPE)
+        if pinned:
+            keep = torch.zeros((64, 8), dtype=torch.int32).pin_memory()
+            out_h = keep.numpy().view(sfcfg.STEP_OUT_DTYPE).reshape(64)
+        else:
+            out_h = np.zeros(64, dtype=sfcfg.STEP_OUT_DTYPE)
         for t in range(120):  # crosses two auto-resets
             act = a.synth_actions(t)
             a.step(act)

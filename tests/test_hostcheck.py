@@ -116,3 +116,32 @@ def test_host_helpers_match_oracle():
     for n in list(range(0, 3000, 7)) + [15000, 999999, 1000000, 1048575]:
         assert np.float32(L.hc_obs_transform_milli(n)).view(np.uint32) == \
             np.float32(sfo.obs_transform(np.float32(n / 1000.0))).view(np.uint32)
+
+
+def test_portal_heavy_stream_matches_oracle(arena_data):
+    """A command stream that keeps building portals and walking into them: humans that wait on an
+    entrance whose exit is taken (HS_ON_ENT, sf_obey) and the exit watch flag of sf_portal_damage
+    (SfDev::misc bit 26) both come and go; every seventh step the whole state is compared."""
+    n, steps, table = 4, 1500, b"]]]]wasdwasdqe+xz[u"
+    cfg = sfcfg.make_config(arena_data, n_envs=n, mode=sfcfg.MODE_SQUAD, level_min=10, auto_reset=False)
+    hs = hostcheck.HostSim(cfg)
+    oracles = common.make_oracles(arena_data, n, sfcfg.MODE_SQUAD, 10)
+    for e in range(n):
+        hs.reset(e, common.synth_tb(e), common.synth_serial(e, 0))
+    alive, watch_seen = [True] * n, set()
+    for t in range(steps):
+        act = common.synth_actions(range(n), 1, t, table)
+        hs.step(act.tobytes())
+        for e, o in enumerate(oracles):
+            if not alive[e]:
+                continue
+            st = o.step(bytes(act[e]))
+            assert hs.step_out(e)["status"] == st, (t, e)
+            if st != sfcfg.RUNNING:
+                alive[e] = False
+                continue
+            watch_seen.add((hs.misc(e) >> 26) & 1)
+            if t % 7 == 0:
+                d0, d1 = o.dump(), hs.dump(e)
+                assert len(d0) == len(d1) and (d0 == d1).all(), (t, e, sfo.diff_records(d0, d1))
+    assert watch_seen == {0, 1}

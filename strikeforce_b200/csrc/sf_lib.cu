@@ -186,15 +186,17 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
  *   1. entity -> window maps for the owning bullets and player-built cells (shared memory);
  *   2. the window is classified; cells that are neither floor nor outside the map go to a
  *      work list, so the per-cell feature code runs on dense lanes (~15% of a window);
- *   3. per tile: wait until the TMA has read the tile's previous content, zero it, write the
- *      features of the listed cells, fence to the async proxy, one thread issues the bulk store. */
+ *   3. per tile: wait until the TMA has read the tile's previous content, write the features of
+ *      the listed cells (the first tile of a window first wipes the cells the window before it
+ *      listed; everything else in the tile is zero and stays zero), fence to the async proxy, one
+ *      thread issues the bulk store. */
 #ifndef SF_OBS_CTA
 #define SF_OBS_CTA 128
 #define SF_OBS_CTAS_PER_SM 5
 #define SF_OBS_HALF_CH 8 /* channels per shared-memory tile (measured: 16/256/3 -> 46%, 8/128/5 -> 51% of HBM peak) */
 #endif
-#define SF_OBS_HALF_FLOATS (SF_OBS_HALF_CH * SF_OBS_CELLS) /* 15,376 floats = 61,504 B, a multiple of 16 */
-#define SF_OBS_SMEM (SF_OBS_HALF_FLOATS * 4 + 3 * 1984 + 16)
+#define SF_OBS_HALF_FLOATS (SF_OBS_HALF_CH * SF_OBS_CELLS) /* 7,688 floats = 30,752 B, a multiple of 16 */
+#define SF_OBS_SMEM (SF_OBS_HALF_FLOATS * 4 + 4 * 1984 + 16)
 
 __device__ __forceinline__ void sf_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
 {
@@ -210,11 +212,16 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
     float *tile = reinterpret_cast<float *>(sf_smem);
     int16_t *bmap = reinterpret_cast<int16_t *>(sf_smem + SF_OBS_HALF_FLOATS * 4);
     int16_t *tmap = bmap + 992;
-    uint16_t *work = reinterpret_cast<uint16_t *>(tmap + 992);
-    int *count = reinterpret_cast<int *>(work + 992);
+    uint16_t *work = reinterpret_cast<uint16_t *>(tmap + 992), *prev = work + 992; /* this window's list, the last one's */
+    int *count = reinterpret_cast<int *>(work + 2 * 992);
     SfTabs t;
     sf_global_tabs(d, t);
     uint32_t fb = 0;
+    int n_prev = 0;
+    /* the tile is zero outside the listed cells at all times: it is cleared once, and a window only
+       wipes what the window before it wrote */
+    for (int i = threadIdx.x; i < SF_OBS_HALF_FLOATS / 4; i += SF_OBS_CTA)
+        reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int env = item / nsel;
         uint32_t m = agent_mask;
@@ -253,10 +260,18 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                 if (tf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
                     tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
             }
-            for (int w = threadIdx.x; w < SF_OBS_CELLS; w += SF_OBS_CTA) {
-                int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
-                if (cell >= 0 && (t.smap[cell] != 0 || SF_G(cell) != 0)) work[atomicAdd(count, 1)] = (uint16_t)w;
+            /* the loads of a thread's eight window cells are issued together, then classified */
+            constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
+            uint32_t cv[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int w = threadIdx.x + q * SF_OBS_CTA;
+                const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
+                cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
             }
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+                if (cv[q]) work[atomicAdd(count, 1)] = (uint16_t)(threadIdx.x + q * SF_OBS_CTA);
         }
         __syncthreads();
         const int n_work = *count;
@@ -266,9 +281,14 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             /* the TMA must have read the tile's previous content before it is overwritten */
             if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncthreads();
-            float4 *h4 = reinterpret_cast<float4 *>(half);
-            for (int i = threadIdx.x; i < SF_OBS_HALF_FLOATS / 4; i += SF_OBS_CTA) h4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
+            if (part == 0) { /* the later tiles of a window overwrite exactly the cells of its first one */
+                for (int i = threadIdx.x; i < n_prev; i += SF_OBS_CTA) {
+                    const int w = prev[i];
+#pragma unroll
+                    for (int c = 0; c < SF_OBS_HALF_CH; ++c) half[c * SF_OBS_CELLS + w] = 0.f;
+                }
+                __syncthreads();
+            }
             for (int i = threadIdx.x; i < n_work; i += SF_OBS_CTA) {
                 const int w = work[i];
                 int32_t f[32];
@@ -283,6 +303,8 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             if (threadIdx.x == 0) sf_bulk_store(out + part * SF_OBS_HALF_FLOATS, half, SF_OBS_HALF_FLOATS * 4);
             static_assert((SF_OBS_HALF_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
         }
+        uint16_t *sw = work;
+        work = prev, prev = sw, n_prev = n_work;
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);

@@ -65,7 +65,9 @@ enum {
 };
 
 /* game modes */
-enum { SF_MODE_SOLO = 0, SF_MODE_TIMER = 1, SF_MODE_SQUAD = 2 };
+enum { SF_MODE_SOLO = 0, SF_MODE_TIMER = 1, SF_MODE_SQUAD = 2,
+       SF_MODE_ROYALE = 3 /* "Battle Royal" / "AI Battle Royal", the online modes, gameplay.hpp:1235 */ };
+#define SF_MAX_PLAYERS 16 /* players of a Battle Royale arena (BASELINE.json configs[4]) */
 
 SF_HD static inline uint64_t sf_mix64(uint64_t x)
 {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 1
+#define SF_ABI_VERSION 2
 
 /* arena geometry of the reference (gameplay.hpp:37: F = 3, N = 30, M = 100) */
 #define SF_FLOORS 3
@@ -66,7 +66,7 @@ typedef struct sf_config {
     int32_t abi_version;             /* SF_ABI_VERSION */
     int32_t n_envs;                  /* arenas held by this handle */
     int64_t env_id_base;             /* global id of local arena 0 (multi-GPU sharding) */
-    int32_t mode;                    /* SF_MODE_SOLO / TIMER / SQUAD */
+    int32_t mode;                    /* SF_MODE_SOLO / TIMER / SQUAD / ROYALE */
     int32_t level_min, level_max;    /* arena e plays level level_min + e % (level_max-level_min+1) */
     int32_t squad_agents;            /* 1: the 9 squad NPCs are driven (USE_AGENT_IN_SQUAD_NPCS,
                                         gameplay.hpp:1886-1901); 0: they idle ('+'), macros.hpp:14 */
@@ -83,6 +83,14 @@ typedef struct sf_config {
     sf_weapon weapons[8];            /* level 0 stats; each owned level applies upgrade(), Item.hpp:105-111 */
     int32_t player_sheet[SF_SHEET_LEN]; /* the account sheet (me.build), Character.hpp:650-709 */
     int32_t npc_sheet[SF_SHEET_LEN];    /* character/human_enemy.txt (gen_human), Character.hpp:662-669 */
+    /* SF_MODE_ROYALE (the reference's online modes as its replay reader plays them,
+       gameplay.hpp:1795-1859): humans 0 .. royale_players-1 are players, every one of them with
+       the player sheet and a command of its own each step (sf_step: actions[env][player], any
+       symbol of the alphabet); player i belongs to team royale_teams[i] (1..7); arena slot 0 is
+       `ind`, the player whose death or victory ends the match.  Each player gets way = rand()%4+1
+       and a rejection-sampled '.' cell; the level is 1 (gameplay.hpp:1641, 1659). */
+    int32_t royale_players;          /* 2..SF_MAX_PLAYERS */
+    int32_t royale_teams[SF_MAX_PLAYERS];
 } sf_config;
 
 typedef struct sf_handle sf_handle;

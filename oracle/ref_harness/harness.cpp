@@ -40,7 +40,7 @@ bool  g_inited = false;
 
 const char *mode_name(int m)
 {
-    return m == SF_MODE_SOLO ? "Solo" : m == SF_MODE_TIMER ? "Timer" : "Squad";
+    return m == SF_MODE_SOLO ? "Solo" : m == SF_MODE_TIMER ? "Timer" : m == SF_MODE_ROYALE ? "Battle Royal" : "Squad";
 }
 
 void track_and_check_caps()
@@ -84,8 +84,11 @@ void eval_end()
 {
     if (g_status != SF_RUNNING)
         return;
+    if (g.online && rivals_dead()) { g_status = SF_WIN; return; }   // first test of check_end(), :1103
     if (hum[ind].get_Hp() <= 0) { g_status = SF_DEAD; return; }
-    if (g_mode == SF_MODE_TIMER) {
+    if (g_mode == SF_MODE_ROYALE) {
+        // an online match ends in no other way
+    } else if (g_mode == SF_MODE_TIMER) {
         if (g.frame >= g.level * 7500)
             g_status = (g.kills < g.level * 5) ? SF_TIMEOUT : SF_WIN;
     } else if (g_mode == SF_MODE_SOLO) {
@@ -202,6 +205,16 @@ int sfref_reset_ex(int mode, int level, const char *player_template, int squad_a
             g.prepare(hum[i]);
             hum[i].agent->slot = i;
         }
+    if (mode == SF_MODE_ROYALE)
+        // Battle Royale through the reference's replay reader (gameplay.hpp:1762-1806, 1847-1859):
+        // the other players are `remote`, their commands come from the file; giving them an oracle
+        // agent changes nothing in the tick (human_action takes the remote branch, :981) and lets
+        // sfref_observe show what each player's own client would see
+        for (int i = 0; i < 64; ++i)
+            if (i != ind && mh[i]) { // right after load_data() the live humans are the players
+                g.prepare(hum[i]);
+                hum[i].agent->slot = i;
+            }
     ++g.frame;
     g_status = SF_RUNNING;
     g_steps = 0;

@@ -62,6 +62,7 @@ typedef struct obullet { int way, cor[3], dcor[3], owner, damage, effect, range,
 struct sfo_arena {
     /* configuration */
     int mode, squad_agents, max_steps;
+    int n_players, teams[SF_MAX_PLAYERS]; /* SF_MODE_ROYALE: `players` and the teams of the replay header */
     int cap_h, cap_z, cap_b, cap_chest, cap_built, cap_portal;
     uint8_t map_cells[SF_CELLS];
     int16_t map_portal[SF_CELLS];
@@ -78,6 +79,7 @@ struct sfo_arena {
     obullet bull[MAXS];
     int portal[MAXS][3];
     uint8_t mb[MAXS], active[MAXS], mz[MAXS], mh[MAXS];
+    uint8_t remote[MAXS]; /* gameplay.hpp:53: slots of the other players of an online match */
     uint8_t command[MAXS];
     /* gameplay.hpp:459-475 */
     int64_t loot, level, teams_kills, kills, chest, frame;
@@ -354,7 +356,7 @@ static int p_ind(const sfo_arena *a)
 static int h_ind(const sfo_arena *a)
 {
     for (int i = 0; i < MAXS; ++i)
-        if (i != a->ind && !a->mh[i]) return i;
+        if (i != a->ind && !a->mh[i] && !a->remote[i]) return i;
     return -1;
 }
 static int z_ind(const sfo_arena *a)
@@ -712,7 +714,8 @@ static void human_action(sfo_arena *a, const uint8_t *agent_cmd, int n_cmd)
 {
     for (int i = 0; i < MAXS; ++i)
         if (i != a->ind && a->mh[i]) {
-            if (a->hum[i].rnpc) a->command[i] = (uint8_t)human_rnpc_bot(a);
+            if (a->remote[i]) a->command[i] = i < n_cmd ? agent_cmd[i] : '+'; /* recieve() / the replay file, :977-986 */
+            else if (a->hum[i].rnpc) a->command[i] = (uint8_t)human_rnpc_bot(a);
             else if (a->hum[i].agent_active && i < n_cmd) a->command[i] = agent_cmd[i];
             else a->command[i] = '+';
         }
@@ -858,6 +861,7 @@ static void setup(sfo_arena *a)
                 }
             }
     a->ind = 0;
+    memset(a->remote, 0, sizeof a->remote);
     a->mh[0] = 1;
     memset(&a->hum[0], 0, sizeof a->hum[0]);
     human_build(&a->hum[0], a->player_sheet, 0); /* hum[ind] = me, me.build(false, "", sheet) */
@@ -880,11 +884,41 @@ static void setup(sfo_arena *a)
             a->hum[i].team = 2;
             a->hum[i].agent_active = a->squad_agents;
         }
+    } else if (a->mode == SF_MODE_ROYALE) {
+        /* load_data(), online branch as the replay reader runs it (:1776-1806): every player's
+           sheet comes from the match header; here they all carry the player sheet.  The cells are
+           drawn after the stream is seeded (place_players) */
+        a->hum[0].team = a->teams[0];
+        for (int i = 1; i < a->n_players; ++i) {
+            memset(&a->hum[i], 0, sizeof a->hum[i]);
+            human_build(&a->hum[i], a->player_sheet, 0);
+            a->hum[i].team = a->teams[i];
+            a->mh[i] = 1;
+            a->remote[i] = 1;
+            a->hum[i].agent_active = 1; /* not the reference's flag: lets sfo_observe show what that player's own client sees */
+        }
     } else {
         a->hum[0].cor[0] = 0, a->hum[0].cor[1] = 1, a->hum[0].cor[2] = 1;
         a->themap[0][1][1].human = 0, a->themap[0][1][1].s[0] = 1;
     }
     a->hum[0].agent_active = 1; /* prepare(me), :1743-1744 */
+}
+
+/* gameplay.hpp:1847-1859: way and a rejection-sampled '.' cell for every player, in index order */
+static void place_players(sfo_arena *a)
+{
+    for (int i = 0; i < a->n_players; ++i) {
+        a->hum[i].way = RAND(a) % 4 + 1;
+        for (;;) {
+            int f = RAND(a) % F, r = RAND(a) % N, c = RAND(a) % M;
+            if (showit(&a->themap[f][r][c]) == '.') {
+                a->themap[f][r][c].human = i;
+                a->themap[f][r][c].s[0] = 1;
+                a->hum[i].cor[0] = f, a->hum[i].cor[1] = r, a->hum[i].cor[2] = c;
+                break;
+            }
+        }
+    }
 }
 
 /* harness track_and_check_caps() */
@@ -920,11 +954,17 @@ static int update_bull_oob(const sfo_arena *a)
 static void eval_end(sfo_arena *a)
 {
     if (a->status != SF_RUNNING) return;
+    if (a->mode == SF_MODE_ROYALE && rivals_are_dead(a)) { /* "online && rivals_are_dead()" comes first, :1103 */
+        a->status = SF_WIN;
+        return;
+    }
     if (a->hum[a->ind].Hp <= 0) {
         a->status = SF_DEAD;
         return;
     }
-    if (a->mode == SF_MODE_TIMER) {
+    if (a->mode == SF_MODE_ROYALE) {
+        /* no other way to end an online match */
+    } else if (a->mode == SF_MODE_TIMER) {
         if (a->frame >= a->level * 7500) a->status = (a->kills < a->level * 5) ? SF_TIMEOUT : SF_WIN;
     } else if (a->mode == SF_MODE_SOLO) {
         if (a->level * 5 <= a->kills) a->status = SF_WIN;
@@ -945,6 +985,11 @@ sfo_arena *sfo_create(const sf_config *cfg)
     sfo_arena *a = (sfo_arena *)calloc(1, sizeof *a);
     if (!a) return NULL;
     a->mode = cfg->mode;
+    if (cfg->mode == SF_MODE_ROYALE) {
+        if (cfg->royale_players < 2 || cfg->royale_players > SF_MAX_PLAYERS) return free(a), (sfo_arena *)NULL;
+        a->n_players = cfg->royale_players;
+        for (int i = 0; i < a->n_players; ++i) a->teams[i] = cfg->royale_teams[i];
+    }
     a->squad_agents = cfg->squad_agents != 0;
     a->max_steps = cfg->max_steps;
     a->cap_h = cfg->cap_humans, a->cap_z = cfg->cap_zombies, a->cap_b = cfg->cap_bullets;
@@ -966,9 +1011,12 @@ void sfo_destroy(sfo_arena *a) { free(a); }
 void sfo_reset(sfo_arena *a, int level, int64_t tb, int64_t serial)
 {
     a->level = level;
+    if (a->mode == SF_MODE_ROYALE) level = 1; /* gameplay.hpp:1641, 1659 */
+    a->level = level;
     setup(a);
     sfo_srand(&a->rng, tb, serial);
     a->jomle0 = a->rng.jomle;
+    if (a->mode == SF_MODE_ROYALE) place_players(a);
     ++a->frame; /* play(): "++frame" before the loop, gameplay.hpp:1441 */
     a->status = SF_RUNNING;
     a->steps = 0;
@@ -1029,6 +1077,7 @@ static int step_b_(sfo_arena *a, const uint8_t *actions, int n)
     int nc = n < 64 ? n : 64;
     for (int i = 0; i < nc; ++i) { /* harness action_index(): symbols outside gameplay::action read '+' */
         cmd[i] = strchr(SF_ACTIONS9, actions[i]) && actions[i] ? actions[i] : '+';
+        if (a->remote[i]) cmd[i] = actions[i]; /* a remote player's command is taken as sent */
     }
     human_action(a, cmd, nc);
     CHECK(a);
@@ -1285,14 +1334,14 @@ long sfo_run_stream(sfo_arena *a, int64_t env, int level, const char *table, int
 {
     static float obs[SF_OBS_LEN];
     int64_t episode = 0;
-    uint64_t streams[10];
-    for (int ag = 0; ag < 10; ++ag) streams[ag] = sf_synth_stream_init(env, ag);
-    int n_agents = (a->mode == SF_MODE_SQUAD && a->squad_agents) ? 10 : 1;
+    uint64_t streams[SF_MAX_PLAYERS];
+    for (int ag = 0; ag < SF_MAX_PLAYERS; ++ag) streams[ag] = sf_synth_stream_init(env, ag);
+    int n_agents = a->mode == SF_MODE_ROYALE ? a->n_players : (a->mode == SF_MODE_SQUAD && a->squad_agents) ? 10 : 1;
     sfo_reset(a, level, sf_synth_tb(env), sf_synth_serial(env, episode));
-    uint8_t act[10];
+    uint8_t act[SF_MAX_PLAYERS];
     uint64_t acc = 0;
     for (long s = 0; s < n_steps; ++s) {
-        for (int ag = 0; ag < 10; ++ag) {
+        for (int ag = 0; ag < SF_MAX_PLAYERS; ++ag) {
             uint64_t z = sf_synth_stream_next(&streams[ag]);
             act[ag] = (uint8_t)table[z % (uint64_t)table_len];
         }

@@ -14,13 +14,14 @@ import numpy as np
 
 from . import data as sfdata
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OBS_CH, OBS_WIN = 32, 31
 OBS_LEN = OBS_CH * OBS_WIN * OBS_WIN
 SHEET_LEN = sfdata.SHEET_LEN
 
-MODE_SOLO, MODE_TIMER, MODE_SQUAD = 0, 1, 2
-MODES = {"Solo": MODE_SOLO, "Timer": MODE_TIMER, "Squad": MODE_SQUAD}
+MODE_SOLO, MODE_TIMER, MODE_SQUAD, MODE_ROYALE = 0, 1, 2, 3
+MODES = {"Solo": MODE_SOLO, "Timer": MODE_TIMER, "Squad": MODE_SQUAD, "Royale": MODE_ROYALE, "Battle Royal": MODE_ROYALE}
+MAX_PLAYERS = 16
 
 RUNNING, WIN, DEAD, TIMEOUT, TRUNCATED, OVERFLOW, UB_GUARD = range(7)
 STATUS_NAMES = ["running", "win", "dead", "timeout", "truncated", "overflow", "ub_guard"]
@@ -71,6 +72,8 @@ class SfConfig(C.Structure):
         ("weapons", Weapon * 8),
         ("player_sheet", C.c_int32 * SHEET_LEN),
         ("npc_sheet", C.c_int32 * SHEET_LEN),
+        ("royale_players", C.c_int32),
+        ("royale_teams", C.c_int32 * MAX_PLAYERS),
     ]
 
 
@@ -85,9 +88,9 @@ DEFAULT_CAPS = dict(cap_humans=64, cap_zombies=128, cap_bullets=96, cap_chests=9
 
 
 def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, level_max=None, squad_agents=False,
-                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None):
+                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None, teams=None):
     """Build an ``sf_config``.  The returned struct keeps the numpy arrays it points to alive
-    (``cfg._keep``)."""
+    (``cfg._keep``).  ``teams`` (Battle Royale only): the team of each player, e.g. ``[1, 1, 2, 2]``."""
     if isinstance(mode, str):
         mode = MODES[mode]
     cfg = SfConfig()
@@ -117,5 +120,13 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
     for i in range(SHEET_LEN):
         cfg.player_sheet[i] = int(sheet[i])
         cfg.npc_sheet[i] = int(arena.npc_sheet[i])
+    if mode == MODE_ROYALE:
+        teams = list(teams if teams is not None else [1 + i % 4 for i in range(MAX_PLAYERS)])
+        if not 2 <= len(teams) <= MAX_PLAYERS:
+            raise ValueError("Battle Royale needs 2..%d players" % MAX_PLAYERS)
+        cfg.royale_players = len(teams)
+        for i, t in enumerate(teams):
+            cfg.royale_teams[i] = int(t)
+        cfg.level_min = cfg.level_max = 1  # gameplay.hpp:1641, 1659
     cfg._keep = (cells, portal)
     return cfg

@@ -53,7 +53,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         uint32_t cp = SF_AT(d.h_cons, h), tp = SF_AT(d.h_thr, h);
         int n = 0, pf, pr, pc;
         sf_tcell_decode((int)(pw & POS_CELL), &pf, &pr, &pc);
-        f[n++] = (int32_t)((e.mh >> h) & 1), f[n++] = (sel & HS_RNPC) ? 1 : 0, f[n++] = (int32_t)(sel & HS_TEAM);
+        f[n++] = (int32_t)((e.mh >> h) & 1), f[n++] = (sel & HS_RNPC) ? 1 : 0, f[n++] = sf_team_value(sel);
         f[n++] = (int32_t)(pw >> POS_HI_SHIFT) + 1;
         f[n++] = pf, f[n++] = pr, f[n++] = pc;
         f[n++] = SF_AT(d.h_hp, h), f[n++] = SF_AT(d.h_mind, h), f[n++] = SF_AT(d.h_stam, h);
@@ -62,7 +62,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         for (int j = 0; j < 4; ++j) f[n++] = (int32_t)((cp >> (8 * j)) & 0xFFu);
         for (int j = 0; j < 4; ++j) f[n++] = (int32_t)((tp >> (8 * j)) & 0xFFu);
         f[n++] = (int32_t)(bp & 0xFFu), f[n++] = (int32_t)((bp >> 8) & 0xFFu), f[n++] = (int32_t)((bp >> 16) & 0xFFu) - 1;
-        f[n++] = h == 0 ? k.player.mindamage_def : k.npc_mindamage_def[e.level];
+        f[n++] = h < k.n_players ? k.player.mindamage_def : k.npc_mindamage_def[e.level];
         sink.elem(SF_K_HUMAN, h, f, SF_NF_HUMAN);
     }
     for (int z = m2_next(e.mz, 0); z >= 0; z = m2_next(e.mz, z + 1)) {

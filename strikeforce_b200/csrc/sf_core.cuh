@@ -337,10 +337,10 @@ SF_FN void sf_install_stream(const SfDev &d, const SfTabs &t, int env, SfEnv &e,
 
 /* ------------------------------------------------------------------ entities */
 
-SF_FN const SfTemplate &sf_tmpl(const SfConst &k, int h) { return h == 0 ? k.player : k.npc; }
+SF_FN const SfTemplate &sf_tmpl(const SfConst &k, int h) { return h < k.n_players ? k.player : k.npc; }
 SF_FN int sf_punch_base(const SfConst &k, const SfEnv &e, int h)
 {
-    return h == 0 ? k.player_punch_base : k.npc_punch_base[e.level];
+    return h < k.n_players ? k.player_punch_base : k.npc_punch_base[e.level];
 }
 
 /* an arena that needs a slot beyond its configured capacity stops (harness: SF_OVERFLOW) */
@@ -356,7 +356,7 @@ SF_FN void sf_init_human(const SfDev &d, int env, const SfTemplate &tp, int h, i
                          bool agent)
 {
     SF_AT(d.h_pw, h) = (uint16_t)cell; /* way = 1 */
-    SF_AT(d.h_sel, h) = (uint16_t)((uint32_t)team | (rnpc ? HS_RNPC : 0u) | (agent ? HS_AGENT : 0u));
+    SF_AT(d.h_sel, h) = (uint16_t)(sf_team_bits(team) | (rnpc ? HS_RNPC : 0u) | (agent ? HS_AGENT : 0u));
     SF_AT(d.h_bp, h) = (uint32_t)tp.blocks | ((uint32_t)tp.portals << 8);
     SF_AT(d.h_hp, h) = tp.hp;
     SF_AT(d.h_mind, h) = tp.mindamage;
@@ -520,7 +520,8 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
                 SF_G(cell) = (uint16_t)(C_S1 | (uint32_t)z);
                 m2_set(e.mz, z);
             } else {
-                int h = sf_ffs64(~(e.mh | 1ull)); /* h_ind skips ind, gameplay.hpp:216-221 */
+                /* h_ind skips ind and the slots of the other players (remote[]), gameplay.hpp:216-221 */
+                int h = sf_ffs64(~(e.mh | ((1ull << k.n_players) - 1ull)));
                 if (h < 0 || h >= k.cap_h) sf_fail_env(e, SF_OVERFLOW);
                 else {
                     sf_init_human(d, env, k.npc, h, cell, true, 0, false);
@@ -1207,7 +1208,9 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
         int c = sf_rnpc_bot(t, e, is_live && (sel & HS_RNPC));
         if (is_live && !(sel & HS_RNPC)) {
             c = '+';
-            if ((sel & HS_AGENT) && h < k.n_agents && actions) {
+            if (k.mode == SF_MODE_ROYALE && h < k.n_players && actions) {
+                c = actions[h]; /* a remote player's command arrives as sent (recieve(), gameplay.hpp:977-986) */
+            } else if ((sel & HS_AGENT) && h < k.n_agents && actions) {
                 c = actions[h];
                 bool ok = c == '+' || c == 'x' || c == 'z' || c == 'q' || c == 'e' || c == 'a' || c == 'w' ||
                           c == 's' || c == 'd';
@@ -1285,6 +1288,10 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         }
         e.mh = 0x3FFull;
         e.hw_h = 10;
+    } else if (k.mode == SF_MODE_ROYALE) {
+        e.level = 1; /* gameplay.hpp:1641, 1659 */
+        e.mh = (1ull << k.n_players) - 1ull;
+        e.hw_h = k.n_players;
     } else {
         int c0 = sf_cell_of(0, 1, 1);
         sf_init_human(d, env, k.player, 0, c0, false, 1, true);
@@ -1294,6 +1301,22 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
     }
     /* the stream of this episode was seeded as the pending one; the next episode's follows */
     sf_install_stream(d, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode + 1));
+    if (k.mode == SF_MODE_ROYALE) {
+        /* load_data(), online branch (gameplay.hpp:1847-1859): in index order every player draws
+           way = rand() % 4 + 1, then cells until one prints '.' */
+        for (int i = 0; i < k.n_players; ++i) {
+            const int way0 = sf_rand(e, t) % 4;
+            int cell;
+            for (;;) {
+                const int f = sf_rand(e, t) % SF_FLOORS, r = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
+                cell = sf_cell_of(f, r, c);
+                if (sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT) break;
+            }
+            sf_init_human(d, env, k.player, i, cell, false, k.teams[i], true);
+            SF_AT(d.h_pw, i) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
+            SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)i);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ the step */
@@ -1303,8 +1326,20 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
 SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
 {
     if (e.on) {
-        if (SF_AT(d.h_hp, 0) <= 0) {
+        bool rivals = false; /* rivals_are_dead, gameplay.hpp:497-505 */
+        if (k.mode == SF_MODE_ROYALE) {
+            uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
+            for (uint64_t m = e.mh; m; m &= m - 1) {
+                uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
+                if (tm && tm != me) rivals = true;
+            }
+        }
+        if (k.mode == SF_MODE_ROYALE && !rivals) {
+            e.status = SF_WIN; /* "online && rivals_are_dead()" is the first test of check_end(), :1103 */
+        } else if (SF_AT(d.h_hp, 0) <= 0) {
             e.status = SF_DEAD;
+        } else if (k.mode == SF_MODE_ROYALE) {
+            /* an online match ends in no other way */
         } else if (k.mode == SF_MODE_TIMER) {
             if ((int64_t)e.frame >= (int64_t)e.level * 7500) e.status = (e.kills < e.level * 5) ? SF_TIMEOUT : SF_WIN;
         } else if (k.mode == SF_MODE_SOLO) {

@@ -122,10 +122,17 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
 {
     if (cfg.abi_version != SF_ABI_VERSION) return "abi_version mismatch";
     if (cfg.n_envs <= 0) return "n_envs must be positive";
-    if (cfg.mode < SF_MODE_SOLO || cfg.mode > SF_MODE_SQUAD) return "unknown mode";
+    if (cfg.mode < SF_MODE_SOLO || cfg.mode > SF_MODE_ROYALE) return "unknown mode";
+    if (cfg.mode == SF_MODE_ROYALE) {
+        if (cfg.royale_players < 2 || cfg.royale_players > SF_MAX_PLAYERS) return "royale_players must be 2..16";
+        if (cfg.level_min != 1 || cfg.level_max != 1) return "Battle Royale is played at level 1 (gameplay.hpp:1641)";
+        for (int i = 0; i < cfg.royale_players; ++i)
+            if (cfg.royale_teams[i] < 1 || cfg.royale_teams[i] > 7) return "royale_teams must be 1..7";
+    }
     if (!cfg.map_cells || !cfg.map_portal) return "map_cells / map_portal missing";
     if (cfg.level_min < 1 || cfg.level_max < cfg.level_min || cfg.level_max > SF_MAX_LEVEL) return "level range";
     if (cfg.cap_humans < 10 || cfg.cap_humans > SF_LIM_HUMANS) return "cap_humans out of range (10..64)";
+    if (cfg.mode == SF_MODE_ROYALE && cfg.cap_humans < cfg.royale_players) return "cap_humans below royale_players";
     if (cfg.cap_zombies < 1 || cfg.cap_zombies > SF_LIM_ZOMBIES) return "cap_zombies out of range (1..128)";
     if (cfg.cap_bullets < 1 || cfg.cap_bullets > SF_LIM_BULLETS) return "cap_bullets out of range (1..128)";
     if (cfg.cap_portals < 1 || cfg.cap_portals > SF_LIM_PORTALS) return "cap_portals out of range (1..128)";
@@ -134,7 +141,9 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     std::memset(&k, 0, sizeof k);
     k.mode = cfg.mode, k.squad_agents = cfg.squad_agents != 0, k.auto_reset = cfg.auto_reset != 0;
     k.max_steps = cfg.max_steps, k.level_min = cfg.level_min, k.level_span = cfg.level_max - cfg.level_min + 1;
-    k.n_agents = (cfg.mode == SF_MODE_SQUAD && cfg.squad_agents) ? 10 : 1;
+    k.n_players = cfg.mode == SF_MODE_ROYALE ? cfg.royale_players : 1;
+    k.n_agents = cfg.mode == SF_MODE_ROYALE ? k.n_players : (cfg.mode == SF_MODE_SQUAD && cfg.squad_agents) ? 10 : 1;
+    for (int i = 0; i < k.n_players && cfg.mode == SF_MODE_ROYALE; ++i) k.teams[i] = (uint8_t)cfg.royale_teams[i];
     k.cap_h = cfg.cap_humans, k.cap_z = cfg.cap_zombies, k.cap_b = cfg.cap_bullets, k.cap_chest = cfg.cap_chests;
     k.cap_t = cfg.cap_built, k.cap_p = cfg.cap_portals;
     k.env_id_base = cfg.env_id_base;

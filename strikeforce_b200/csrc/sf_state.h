@@ -80,14 +80,17 @@ enum { K_NONE = 0, K_CHEST0 = 1, K_BLOCK = 5, K_ENTRANCE = 6, K_EXIT = 7 };
 /* what node::showit() prints (gameplay.hpp:321-341) */
 enum { SH_WALL, SH_HUMAN, SH_ZOMBIE, SH_UP, SH_DOWN, SH_BULLET, SH_CHEST, SH_EXIT, SH_DOT };
 
-/* human word h_sel: team | rnpc | agent | vec+1 | ind+1 | on-entrance */
-#define HS_TEAM 0x0003u
+/* human word h_sel: team | rnpc | agent | vec+1 | ind+1 | on-entrance | team bit 2.  A team is 0
+ * (NPC humans) .. 7; its bits are only ever compared, sf_team_bits / sf_team_value convert. */
+#define HS_TEAM 0x0803u
 #define HS_RNPC 0x0004u
 #define HS_AGENT 0x0008u
 #define HS_VEC_SHIFT 4 /* 2 bits, stores vec + 1 */
 #define HS_IND_SHIFT 6 /* 4 bits, stores ind + 1 */
 #define HS_ON_ENT 0x0400u /* stands on a player-built entrance whose exit was taken (sf_obey) */
-#define HS_KEEP (0x000Fu | HS_ON_ENT) /* what a new selection leaves alone */
+#define HS_KEEP (0x080Fu | HS_ON_ENT) /* what a new selection leaves alone */
+#define sf_team_bits(team) ((((uint32_t)(team)) & 3u) | ((((uint32_t)(team)) & 4u) << 9))
+#define sf_team_value(sel) ((int32_t)((((uint32_t)(sel)) & 3u) | ((((uint32_t)(sel)) >> 9) & 4u)))
 /* position words: cell id in bits 0-13, (way - 1) or `super` in bits 14-15 */
 #define POS_CELL 0x3FFFu
 #define POS_HI_SHIFT 14
@@ -119,6 +122,8 @@ typedef struct SfTemplate {
 /* constants shared by every arena of a handle (kernel parameter) */
 typedef struct SfConst {
     int32_t mode, squad_agents, auto_reset, max_steps, level_min, level_span, n_agents;
+    int32_t n_players;                      /* humans 0 .. n_players-1 carry the player sheet (1 except in Battle Royale) */
+    uint8_t teams[SF_MAX_PLAYERS];          /* Battle Royale: team of each player */
     int32_t cap_h, cap_z, cap_b, cap_chest, cap_t, cap_p;
     int64_t env_id_base;
     int32_t n_static_exits;

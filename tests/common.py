@@ -45,3 +45,16 @@ def make_oracles(arena_data, n_envs, mode, level, squad_agents=False, player="ac
         a.reset(level, synth_tb(ge), synth_serial(ge, 0))
         arenas.append(a)
     return arenas
+
+
+CAP_KEYS = ("cap_humans", "cap_zombies", "cap_bullets", "cap_chests", "cap_built", "cap_portals")
+
+
+def golden_kwargs(g):
+    """make_config / BatchedArena keyword arguments of a tests/golden fixture (the Battle Royale
+    ones also carry the teams of their players and the capacities they were played with)."""
+    kw = dict(mode=int(g["mode"]), squad_agents=bool(g["squad_agents"]), player=str(g["player"]))
+    if "teams" in g:
+        kw["teams"] = [int(t) for t in g["teams"]]
+        kw["caps"] = dict(zip(CAP_KEYS, (int(c) for c in g["caps"])))
+    return kw

@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Generate tests/golden/royale_*.npz: Battle Royale matches played by the UNMODIFIED reference
+(oracle/_ref/libsfref.so) through its own replay reader -- the one way the reference runs its online
+modes without a match server (gameplay.hpp:1762-1806, 1847-1859, 966-986).
+
+The replay file must list, step by step, the command of `ind` and of every other player alive when
+human_action runs; which players are alive is taken from the C model (oracle/sf_oracle.c) while the
+file is written.  The fixture itself -- status, state hash after every step, observations -- is what
+the reference then produces from that file; had the model been wrong about a death, the reference
+would read a shifted command stream and the two would part within a step.
+Run in the build container (needs oracle/_ref)."""
+import os
+import sys
+import tempfile
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sfo  # noqa: E402
+import sfref  # noqa: E402
+from strikeforce_b200 import config as sfcfg  # noqa: E402
+from strikeforce_b200 import data as sfdata  # noqa: E402
+from strikeforce_b200 import replay  # noqa: E402
+
+CAPS = dict(sfcfg.DEFAULT_CAPS, cap_portals=128, cap_built=1000, cap_bullets=128)
+CAP_KEYS = ("cap_humans", "cap_zombies", "cap_bullets", "cap_chests", "cap_built", "cap_portals")
+
+# name, teams, tb, serial, steps
+CASES = [
+    ("royale_16p_4teams", [1, 2, 3, 4] * 4, 1700000123, 424242, 1000),
+    ("royale_4p_2teams", [1, 2, 2, 1], 1700000777, 31337, 2500),
+]
+
+
+def main(which):
+    """One match per process: the reference keeps its humans in globals, and a slot that held a
+    player of team 3 in the match before would hand that team to the NPC spawned into it."""
+    arena = sfdata.load_default()
+    sheet = arena.player_sheet("account1")
+    for name, teams, tb, serial, steps in [CASES[which]]:
+        P = len(teams)
+        rng = np.random.default_rng(zlib.crc32(name.encode()))
+        table = np.frombuffer(bytes(sfcfg.ACTIONS28), dtype=np.uint8)
+        actions = table[rng.integers(len(table), size=(steps, P))]
+        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS)
+        o = sfo.Arena(cfg)
+        o.reset(1, tb, serial)
+        file_cmds = bytearray()
+        n = 0
+        for t in range(steps):
+            if o.step_a() != 0:
+                break
+            rec = sfo.parse_record(o.dump())
+            file_cmds.append(actions[t, 0])
+            file_cmds.extend(actions[t, i] for i in range(1, P) if rec[(3, i)][0])
+            n = t + 1
+            if o.step_b(bytes(actions[t])) != 0:
+                break
+        path = os.path.join(tempfile.mkdtemp(), name + ".sf_sample")
+        replay.write_royale(path, tb, serial, sheet, teams, bytes(file_cmds))
+        sfref.reset_replay(sfcfg.MODE_ROYALE, 1, path, caps=[CAPS[k] for k in CAP_KEYS])
+        status = np.zeros(n, dtype=np.int32)
+        hashes = np.zeros(n + 1, dtype=np.uint64)
+        hashes[0] = sfref.state_hash()
+        obs, obs_steps, obs_last, records, rec_steps = [], [], [], [], []
+        for t in range(n):
+            if t % 100 == 0:
+                obs.append(sfref.observe(0))
+                try:
+                    obs_last.append(sfref.observe(P - 1))
+                except RuntimeError:  # that player is dead: its agent is gone
+                    obs_last.append(np.full(sfref.OBS_LEN, np.nan, dtype=np.float32))
+                obs_steps.append(t)
+            status[t] = sfref.step(b"+" * P)  # in replay mode every command comes from the file
+            hashes[t + 1] = sfref.state_hash()
+            if t % 250 == 249 or status[t] != 0:
+                records.append(sfref.dump())
+                rec_steps.append(t)
+            if status[t] != 0:
+                status, hashes = status[:t + 1], hashes[:t + 2]
+                break
+        actions = actions[:len(status)]
+        assert o.status() == status[-1] and np.uint64(o.state_hash()) == hashes[-1] or status[-1] in (5, 6)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), mode=sfcfg.MODE_ROYALE, level=1, tb=tb, serial=serial,
+                            squad_agents=0, player="account1", teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
+                            actions=actions, status=status, hashes=hashes, records=np.concatenate(records),
+                            rec_len=np.array([len(r) for r in records], dtype=np.int64), rec_steps=np.array(rec_steps),
+                            obs=np.stack(obs), obs_last=np.stack(obs_last), obs_steps=np.array(obs_steps),
+                            counters=np.array(list(sfref.counters().values())),
+                            population=np.array(list(sfref.population().values())))
+        print(name, "steps", len(status), "final status", int(status[-1]), sfref.population(), sfref.counters())
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        main(int(sys.argv[1]))
+    else:
+        import subprocess
+        for i in range(len(CASES)):
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), str(i)])

@@ -46,7 +46,8 @@ def test_no_cpu_fallback(arena_data):
 def test_struct_layout_matches_header():
     assert C.sizeof(sfcfg.StepOut) == 32
     assert sfcfg.SfConfig.map_cells.offset % 8 == 0
-    assert C.sizeof(sfcfg.SfConfig) == sfcfg.SfConfig.npc_sheet.offset + 4 * sfcfg.SHEET_LEN
+    assert sfcfg.SfConfig.royale_players.offset == sfcfg.SfConfig.npc_sheet.offset + 4 * sfcfg.SHEET_LEN
+    assert C.sizeof(sfcfg.SfConfig) == sfcfg.SfConfig.royale_teams.offset + 4 * sfcfg.MAX_PLAYERS + 4  # tail padding to 8
 
 
 def test_default_arena_and_reference_parser(arena_data, tmp_path):

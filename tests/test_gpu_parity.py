@@ -158,19 +158,22 @@ def test_golden_matches_through_the_c_abi(torch_cuda, arena_data):
         if path.endswith("kat.npz"):
             continue
         g = np.load(path)
-        sim = BatchedArena(33, mode=int(g["mode"]), level=int(g["level"]), squad_agents=bool(g["squad_agents"]),
-                           auto_reset=False, player=str(g["player"]))
+        sim = BatchedArena(33, level=int(g["level"]), auto_reset=False, **common.golden_kwargs(g))
         try:
             e = 32  # the last arena of a partly filled warp
             sim.reset([e], [int(g["tb"])], [int(g["serial"])])
             assert np.uint64(sim.state_hash()[e].item() & 0xFFFFFFFFFFFFFFFF) == g["hashes"][0]
             obs = dict(zip(g["obs_steps"].tolist(), g["obs"]))
+            obs_last = dict(zip(g["obs_steps"].tolist(), g["obs_last"])) if "obs_last" in g else {}
             act = torch_cuda.full((33, sim.n_agents), ord("+"), dtype=torch_cuda.uint8, device=sim.device)
             hashes = []
             for t, a in enumerate(g["actions"]):
                 if t in obs:
                     o = sim.observe(1)[e].reshape(-1).cpu().numpy()
                     assert (o.view(np.uint32) == obs[t].view(np.uint32)).all(), "%s observation step %d" % (path, t)
+                if t in obs_last and not np.isnan(obs_last[t][0]):  # Battle Royale: the last player's view
+                    o = sim.observe(1 << (sim.n_agents - 1))[e].reshape(-1).cpu().numpy()
+                    assert (o.view(np.uint32) == obs_last[t].view(np.uint32)).all(), "%s last player, step %d" % (path, t)
                 act[e] = torch_cuda.from_numpy(a.copy()).to(sim.device)
                 sim.step(act)
                 hashes.append(sim.state_hash()[e:e + 1])

@@ -20,16 +20,19 @@ CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not p.ends
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_device_tick_matches_reference_golden(path, arena_data):
     g = np.load(path)
-    cfg = sfcfg.make_config(arena_data, n_envs=2, mode=int(g["mode"]), level_min=int(g["level"]),
-                            squad_agents=bool(g["squad_agents"]), player=str(g["player"]), auto_reset=False)
+    cfg = sfcfg.make_config(arena_data, n_envs=2, level_min=int(g["level"]), auto_reset=False, **common.golden_kwargs(g))
     hs = hostcheck.HostSim(cfg)
     hs.reset(1, int(g["tb"]), int(g["serial"]))  # arena 1 plays the golden match, arena 0 another one
     assert np.uint64(hs.state_hash(1)) == g["hashes"][0]
     obs = dict(zip(g["obs_steps"].tolist(), g["obs"]))
+    obs_last = dict(zip(g["obs_steps"].tolist(), g["obs_last"])) if "obs_last" in g else {}
     idle = bytes(b"+" * hs.n_agents)
     for t, act in enumerate(g["actions"]):
         if t in obs:
             assert (hs.observe(1, 0).view(np.uint32) == obs[t].view(np.uint32)).all(), "observation, step %d" % t
+        if t in obs_last and not np.isnan(obs_last[t][0]):
+            got = hs.observe(1, hs.n_agents - 1)
+            assert (got.view(np.uint32) == obs_last[t].view(np.uint32)).all(), "observation of the last player, step %d" % t
         hs.step(idle + bytes(act))
         assert hs.status(1) == g["status"][t], "status, step %d" % t
         assert np.uint64(hs.state_hash(1)) == g["hashes"][t + 1], "state hash, step %d" % t

@@ -16,7 +16,8 @@ same names take whole batches:
 
 ``play`` is the loop of ``gameplay::play()`` (gameplay.hpp:1443-1472) for a batch: P1 observation
 and the player's command at the loop top (``get_my_action``, :956); with agent-driven squad
-humans the step is split so that they observe at P2 (``get_command``, :933).
+humans the step is split so that they observe at P2 (``get_command``, :933); in Battle Royale all
+players observe at the loop top, each from its own position (BASELINE.json configs[4]).
 """
 from __future__ import annotations
 
@@ -92,6 +93,14 @@ def play(sim, custom: Custom, steps: int):
     custom.prepare(sim)
     actions = torch.full((sim.n_envs, sim.n_agents), ord("+"), dtype=torch.uint8, device=sim.device)
     squad_mask = ((1 << sim.n_agents) - 1) & ~1
+    if sim.cfg.mode == sfcfg.MODE_ROYALE:
+        # Battle Royale: every player is the `ind` of its own client and observes at the loop top
+        # (get_my_action, :956); the commands of the others arrive over the wire (:977-986)
+        for _ in range(steps):
+            actions[:] = custom.bot(sim, (1 << sim.n_agents) - 1, sfcfg.OBS_P1)
+            sim.step(actions)
+            custom.view(sim)
+        return sim.stats()
     for _ in range(steps):
         actions[:, 0:1] = custom.bot(sim, 1, sfcfg.OBS_P1)  # get_my_action, :956
         if squad_mask:

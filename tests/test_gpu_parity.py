@@ -244,18 +244,18 @@ def test_replay_of_sf_sample_logs(torch_cuda, arena_data, tmp_path):
 
 
 def _sampled_parity(torch, arena_data, n_envs, mode, level_min, level_max, steps, table, sample, player="account1",
-                    squad_agents=False, obs_at=()):
+                    squad_agents=False, obs_at=(), teams=None, obs_mask=1):
     """BASELINE.json-size batches: every arena steps on the GPU, a sample of them is followed by the
     oracle state for state (the whole-batch property: a checksum of all state hashes is finite work
     for the GPU only; the oracle cannot follow 10^5 arenas)."""
     from strikeforce_b200.sim import BatchedArena
     sim = BatchedArena(n_envs, mode=mode, level=level_min, level_max=level_max, squad_agents=squad_agents,
-                       auto_reset=False, player=player)
+                       auto_reset=False, player=player, teams=teams)
     span = level_max - level_min + 1
     oracles = {}
     for e in sample:
         lvl = level_min + e % span
-        cfg = sfcfg.make_config(arena_data, mode=mode, level_min=lvl, squad_agents=squad_agents, player=player)
+        cfg = sfcfg.make_config(arena_data, mode=mode, level_min=lvl, squad_agents=squad_agents, player=player, teams=teams)
         o = sfo.Arena(cfg)
         o.reset(lvl, common.synth_tb(e), common.synth_serial(e, 0))
         oracles[e] = o
@@ -263,12 +263,18 @@ def _sampled_parity(torch, arena_data, n_envs, mode, level_min, level_max, steps
     try:
         for t in range(steps):
             if t in obs_at:
-                obs = sim.observe(1)
-                picked = obs[idx].reshape(len(sample), -1).cpu().numpy()
+                slots = [b for b in range(32) if (obs_mask >> b) & 1]
+                obs = sim.observe(obs_mask)
+                picked = obs[idx].reshape(len(sample), len(slots), -1).cpu().numpy()
                 del obs
                 for i, e in enumerate(sample):
-                    assert (picked[i].view(np.uint32) == oracles[e].observe(0).view(np.uint32)).all(), \
-                        "observation differs: env %d step %d" % (e, t)
+                    for j, slot in enumerate(slots):
+                        try:
+                            ref = oracles[e].observe(slot)
+                        except RuntimeError:  # that human died: its agent is gone (deleteAgent)
+                            continue
+                        assert (picked[i, j].view(np.uint32) == ref.view(np.uint32)).all(), \
+                            "observation differs: env %d slot %d step %d" % (e, slot, t)
             act = sim.synth_actions(t, table)
             sim.step(act)
             h = sim.state_hash()[idx].cpu().numpy().view(np.uint64)
@@ -311,6 +317,32 @@ def test_config4_squad_shard_131072_sampled(torch_cuda, arena_data):
     rng = np.random.default_rng(4)
     sample = sorted(set(rng.integers(0, 131072, size=158).tolist()) | {0, 131071})
     _sampled_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 100, sfcfg.ACTIONS28, sample)
+
+
+def test_config5_royale_32768_sampled(torch_cuda, arena_data):
+    """configs[4] on the reference's map: Battle Royale placement (gameplay.hpp:1847-1859), 16 players
+    in 4 teams, one GPU's shard (32,768 arenas) of the 262,144-arena batch; 96 sampled arenas followed
+    by the oracle, observations of three players of every sampled arena compared bit for bit."""
+    rng = np.random.default_rng(5)
+    sample = sorted(set(rng.integers(0, 32768, size=94).tolist()) | {0, 32767})
+    _sampled_parity(torch_cuda, arena_data, 32768, sfcfg.MODE_ROYALE, 1, 1, 80, sfcfg.ACTIONS28, sample,
+                    teams=[1, 2, 3, 4] * 4, obs_at=(0, 79), obs_mask=(1 << 0) | (1 << 6) | (1 << 15))
+
+
+def test_royale_policy_loop(torch_cuda, arena_data):
+    """configs[4]: observations of all 16 players -> one batched AgentModel forward per tick -> the 16
+    commands of every arena, without leaving the device."""
+    from strikeforce_b200 import bots, policy
+    from strikeforce_b200.sim import BatchedArena
+    torch = torch_cuda
+    torch.manual_seed(0)
+    sim = BatchedArena(48, mode="Royale", teams=[1, 2, 3, 4] * 4, auto_reset=True, max_steps=20)
+    try:
+        agent = policy.PolicyAgent(policy.AgentModel(), 48 * 16, device=sim.device, seed=3)
+        stats = bots.play(sim, bots.Custom(agent), 8)
+        assert stats["steps"] + stats["overflows"] + stats["ub_guards"] == 48 * 8
+    finally:
+        sim.close()
 
 
 def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):

@@ -119,18 +119,29 @@ class PolicyAgent:
     observations of ``sf_observe`` and samples an action per row with a seeded device generator
     (the reference samples with std::random_device, which cannot be reproduced)."""
 
-    def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False):
+    def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False, chunk=0):
         self.model = model.to(device).eval()
         self.state = model.initial_state(batch, device)
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed)
         self.training = training
+        self.chunk = chunk  # >0: rows per forward call (bounds the activations of very large batches)
 
     @torch.no_grad()
     def predict(self, obs):
-        p, _, st = self.model(obs, self.state)
-        act = torch.multinomial(p, 1, generator=self.gen).view(-1)
-        self.state = AgentModel.with_action(st, act)
+        B = obs.shape[0]
+        if not self.chunk or B <= self.chunk:
+            p, _, st = self.model(obs, self.state)
+            act = torch.multinomial(p, 1, generator=self.gen).view(-1)
+            self.state = AgentModel.with_action(st, act)
+            return act
+        act = torch.empty(B, dtype=torch.int64, device=obs.device)
+        for lo in range(0, B, self.chunk):
+            hi = min(B, lo + self.chunk)
+            p, _, st = self.model(obs[lo:hi], tuple(s[lo:hi] for s in self.state))
+            act[lo:hi] = torch.multinomial(p, 1, generator=self.gen).view(-1)
+            for dst, src in zip(self.state, AgentModel.with_action(st, act[lo:hi])):
+                dst[lo:hi] = src
         return act
 
     def update(self, actions, imitate):

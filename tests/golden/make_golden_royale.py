@@ -29,10 +29,13 @@ from strikeforce_b200 import replay  # noqa: E402
 CAPS = dict(sfcfg.DEFAULT_CAPS, cap_portals=128, cap_built=1000, cap_bullets=128)
 CAP_KEYS = ("cap_humans", "cap_zombies", "cap_bullets", "cap_chests", "cap_built", "cap_portals")
 
-# name, teams, tb, serial, steps
+# name, teams, tb, serial, steps, player sheet (the two short matches run until they end: one is won
+# -- every rival dead --, one is lost)
 CASES = [
-    ("royale_16p_4teams", [1, 2, 3, 4] * 4, 1700000123, 424242, 1000),
-    ("royale_4p_2teams", [1, 2, 2, 1], 1700000777, 31337, 2500),
+    ("royale_16p_4teams", [1, 2, 3, 4] * 4, 1700000123, 424242, 1000, "account1"),
+    ("royale_4p_2teams", [1, 2, 2, 1], 1700000777, 31337, 2500, "account1"),
+    ("royale_2p_newplayer_a", [1, 2], 1700000003, 1015, 8000, "new_player"),
+    ("royale_3p_newplayer_b", [1, 2, 2], 1700000002, 2002, 8000, "new_player"),
 ]
 
 
@@ -40,13 +43,13 @@ def main(which):
     """One match per process: the reference keeps its humans in globals, and a slot that held a
     player of team 3 in the match before would hand that team to the NPC spawned into it."""
     arena = sfdata.load_default()
-    sheet = arena.player_sheet("account1")
-    for name, teams, tb, serial, steps in [CASES[which]]:
+    for name, teams, tb, serial, steps, player in [CASES[which]]:
+        sheet = arena.player_sheet(player)
         P = len(teams)
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         table = np.frombuffer(bytes(sfcfg.ACTIONS28), dtype=np.uint8)
         actions = table[rng.integers(len(table), size=(steps, P))]
-        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS)
+        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS, player=player)
         o = sfo.Arena(cfg)
         o.reset(1, tb, serial)
         file_cmds = bytearray()
@@ -86,7 +89,7 @@ def main(which):
         actions = actions[:len(status)]
         assert o.status() == status[-1] and np.uint64(o.state_hash()) == hashes[-1] or status[-1] in (5, 6)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), mode=sfcfg.MODE_ROYALE, level=1, tb=tb, serial=serial,
-                            squad_agents=0, player="account1", teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
+                            squad_agents=0, player=player, teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
                             actions=actions, status=status, hashes=hashes, records=np.concatenate(records),
                             rec_len=np.array([len(r) for r in records], dtype=np.int64), rec_steps=np.array(rec_steps),
                             obs=np.stack(obs), obs_last=np.stack(obs_last), obs_steps=np.array(obs_steps),

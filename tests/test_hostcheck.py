@@ -148,3 +148,31 @@ def test_portal_heavy_stream_matches_oracle(arena_data):
                 d0, d1 = o.dump(), hs.dump(e)
                 assert len(d0) == len(d1) and (d0 == d1).all(), (t, e, sfo.diff_records(d0, d1))
     assert watch_seen == {0, 1}
+
+
+def test_royale_auto_reset_follows_the_seed_chain(arena_data):
+    """Battle Royale with auto-reset: every new episode seeds the next stream of the chain and then
+    draws the players' ways and cells from it (gameplay.hpp:1847-1859)."""
+    teams, n, base, max_steps, steps = [1, 2, 2, 1, 3], 3, 7, 60, 200
+    cfg = sfcfg.make_config(arena_data, n_envs=n, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=True,
+                            max_steps=max_steps, env_id_base=base)
+    hs = hostcheck.HostSim(cfg)
+    ocfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, max_steps=max_steps)
+    oracles = []
+    for e in range(n):
+        o = sfo.Arena(ocfg)
+        o.reset(1, common.synth_tb(base + e), common.synth_serial(base + e, 0))
+        oracles.append(o)
+    episode = [0] * n
+    for t in range(steps):
+        act = common.synth_actions(range(base, base + n), len(teams), t, sfcfg.ACTIONS28)
+        hs.step(act.tobytes())
+        for e, o in enumerate(oracles):
+            st = o.step(bytes(act[e]))
+            assert hs.step_out(e)["status"] == st
+            if st != sfcfg.RUNNING:
+                episode[e] += 1
+                o.reset(1, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
+            d0, d1 = o.dump(), hs.dump(e)
+            assert len(d0) == len(d1) and (d0 == d1).all(), sfo.diff_records(d0, d1)
+    assert hs.stats()["episodes"] == sum(episode) == 9

@@ -85,12 +85,15 @@ typedef struct sf_config {
     int32_t npc_sheet[SF_SHEET_LEN];    /* character/human_enemy.txt (gen_human), Character.hpp:662-669 */
     /* SF_MODE_ROYALE (the reference's online modes as its replay reader plays them,
        gameplay.hpp:1795-1859): humans 0 .. royale_players-1 are players, every one of them with
-       the player sheet and a command of its own each step (sf_step: actions[env][player], any
+       a sheet and a command of their own each step (sf_step: actions[env][player], any
        symbol of the alphabet); player i belongs to team royale_teams[i] (1..7); arena slot 0 is
-       `ind`, the player whose death or victory ends the match.  Each player gets way = rand()%4+1
-       and a rejection-sampled '.' cell; the level is 1 (gameplay.hpp:1641, 1659). */
+       `ind`, the player whose death or victory ends the match: it carries player_sheet (hum[ind] =
+       me), player i > 0 the sheet royale_sheets[i] it announced (get_info / scan_file,
+       gameplay.hpp:131-149, 1797-1806).  Each player gets way = rand()%4+1 and a rejection-sampled
+       '.' cell; the level is 1 (gameplay.hpp:1641, 1659). */
     int32_t royale_players;          /* 2..SF_MAX_PLAYERS */
     int32_t royale_teams[SF_MAX_PLAYERS];
+    int32_t royale_sheets[SF_MAX_PLAYERS][SF_SHEET_LEN]; /* row 0 is not read */
 } sf_config;
 
 typedef struct sf_handle sf_handle;

@@ -63,6 +63,7 @@ struct sfo_arena {
     /* configuration */
     int mode, squad_agents, max_steps;
     int n_players, teams[SF_MAX_PLAYERS]; /* SF_MODE_ROYALE: `players` and the teams of the replay header */
+    int32_t royale_sheets[SF_MAX_PLAYERS][SF_SHEET_LEN]; /* the sheets the other players announced */
     int cap_h, cap_z, cap_b, cap_chest, cap_built, cap_portal;
     uint8_t map_cells[SF_CELLS];
     int16_t map_portal[SF_CELLS];
@@ -886,12 +887,12 @@ static void setup(sfo_arena *a)
         }
     } else if (a->mode == SF_MODE_ROYALE) {
         /* load_data(), online branch as the replay reader runs it (:1776-1806): every player's
-           sheet comes from the match header; here they all carry the player sheet.  The cells are
-           drawn after the stream is seeded (place_players) */
+           sheet comes from the match header.  The cells are drawn after the stream is seeded
+           (place_players) */
         a->hum[0].team = a->teams[0];
         for (int i = 1; i < a->n_players; ++i) {
             memset(&a->hum[i], 0, sizeof a->hum[i]);
-            human_build(&a->hum[i], a->player_sheet, 0);
+            human_build(&a->hum[i], a->royale_sheets[i], 0);
             a->hum[i].team = a->teams[i];
             a->mh[i] = 1;
             a->remote[i] = 1;
@@ -989,6 +990,7 @@ sfo_arena *sfo_create(const sf_config *cfg)
         if (cfg->royale_players < 2 || cfg->royale_players > SF_MAX_PLAYERS) return free(a), (sfo_arena *)NULL;
         a->n_players = cfg->royale_players;
         for (int i = 0; i < a->n_players; ++i) a->teams[i] = cfg->royale_teams[i];
+        memcpy(a->royale_sheets, cfg->royale_sheets, sizeof a->royale_sheets);
     }
     a->squad_agents = cfg->squad_agents != 0;
     a->max_steps = cfg->max_steps;

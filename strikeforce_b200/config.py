@@ -74,6 +74,7 @@ class SfConfig(C.Structure):
         ("npc_sheet", C.c_int32 * SHEET_LEN),
         ("royale_players", C.c_int32),
         ("royale_teams", C.c_int32 * MAX_PLAYERS),
+        ("royale_sheets", (C.c_int32 * SHEET_LEN) * MAX_PLAYERS),
     ]
 
 
@@ -88,9 +89,11 @@ DEFAULT_CAPS = dict(cap_humans=64, cap_zombies=128, cap_bullets=96, cap_chests=9
 
 
 def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, level_max=None, squad_agents=False,
-                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None, teams=None):
+                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None, teams=None, sheets=None):
     """Build an ``sf_config``.  The returned struct keeps the numpy arrays it points to alive
-    (``cfg._keep``).  ``teams`` (Battle Royale only): the team of each player, e.g. ``[1, 1, 2, 2]``."""
+    (``cfg._keep``).  Battle Royale only: ``teams`` = the team of each player, e.g. ``[1, 1, 2, 2]``;
+    ``sheets`` = the character sheet of each player (names or int32[32] arrays; default: every
+    player carries ``player``; entry 0 is the sheet of ``ind`` and replaces ``player``)."""
     if isinstance(mode, str):
         mode = MODES[mode]
     cfg = SfConfig()
@@ -116,7 +119,12 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
         cfg.throwables[i] = Weapon(*[int(v) for v in arena.throwables[i]])
     for i in range(8):
         cfg.weapons[i] = Weapon(*[int(v) for v in arena.weapons[i]])
-    sheet = arena.player_sheet(player) if isinstance(player, str) else np.asarray(player, dtype=np.int32)
+    def as_sheet(x):
+        return arena.player_sheet(x) if isinstance(x, str) else np.asarray(x, dtype=np.int32)
+
+    if mode == MODE_ROYALE and sheets is not None:
+        player = sheets[0]
+    sheet = as_sheet(player)
     for i in range(SHEET_LEN):
         cfg.player_sheet[i] = int(sheet[i])
         cfg.npc_sheet[i] = int(arena.npc_sheet[i])
@@ -125,8 +133,13 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
         if not 2 <= len(teams) <= MAX_PLAYERS:
             raise ValueError("Battle Royale needs 2..%d players" % MAX_PLAYERS)
         cfg.royale_players = len(teams)
+        if sheets is not None and len(sheets) != len(teams):
+            raise ValueError("one sheet per player")
         for i, t in enumerate(teams):
             cfg.royale_teams[i] = int(t)
+            sh = sheet if sheets is None else as_sheet(sheets[i])
+            for j in range(SHEET_LEN):
+                cfg.royale_sheets[i][j] = int(sh[j])
         cfg.level_min = cfg.level_max = 1  # gameplay.hpp:1641, 1659
     cfg._keep = (cells, portal)
     return cfg

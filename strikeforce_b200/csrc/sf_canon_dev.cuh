@@ -62,7 +62,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         for (int j = 0; j < 4; ++j) f[n++] = (int32_t)((cp >> (8 * j)) & 0xFFu);
         for (int j = 0; j < 4; ++j) f[n++] = (int32_t)((tp >> (8 * j)) & 0xFFu);
         f[n++] = (int32_t)(bp & 0xFFu), f[n++] = (int32_t)((bp >> 8) & 0xFFu), f[n++] = (int32_t)((bp >> 16) & 0xFFu) - 1;
-        f[n++] = h < k.n_players ? k.player.mindamage_def : k.npc_mindamage_def[e.level];
+        f[n++] = h < k.n_players ? k.players[h].mindamage_def : k.npc_mindamage_def[e.level];
         sink.elem(SF_K_HUMAN, h, f, SF_NF_HUMAN);
     }
     for (int z = m2_next(e.mz, 0); z >= 0; z = m2_next(e.mz, z + 1)) {

@@ -19,10 +19,12 @@
 
 #ifdef __CUDACC__
 #define SF_FN __device__ __forceinline__
+#define SF_COLD __device__ __noinline__ /* rare paths stay out of the step kernel's hot code */
 #define SF_MFN __device__ __forceinline__
 #define SF_UNROLL _Pragma("unroll")
 #else
 #define SF_FN static inline
+#define SF_COLD static
 #define SF_MFN inline
 #define SF_UNROLL
 #endif
@@ -337,10 +339,10 @@ SF_FN void sf_install_stream(const SfDev &d, const SfTabs &t, int env, SfEnv &e,
 
 /* ------------------------------------------------------------------ entities */
 
-SF_FN const SfTemplate &sf_tmpl(const SfConst &k, int h) { return h < k.n_players ? k.player : k.npc; }
+SF_FN const SfTemplate &sf_tmpl(const SfConst &k, int h) { return h < k.n_players ? k.players[h] : k.npc; }
 SF_FN int sf_punch_base(const SfConst &k, const SfEnv &e, int h)
 {
-    return h < k.n_players ? k.player_punch_base : k.npc_punch_base[e.level];
+    return h < k.n_players ? k.player_punch_base[h] : k.npc_punch_base[e.level];
 }
 
 /* an arena that needs a slot beyond its configured capacity stops (harness: SF_OVERFLOW) */
@@ -1259,6 +1261,31 @@ SF_FN void sf_clear_grid(uint16_t *g)
 #endif
 }
 
+/* load_data(), online branch (gameplay.hpp:1847-1859): in index order every player draws
+ * way = rand() % 4 + 1, then cells until one prints '.' */
+SF_FN void sf_royale_place(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
+{
+    /* one draw site: stage 0 = way, 1..3 = floor, row, column of the next try */
+    int i = 0, stage = 0, way0 = 0, f = 0, r = 0;
+#pragma unroll 1
+    while (i < k.n_players) {
+        const int v = sf_rand(e, t);
+        if (stage == 0) way0 = v % 4, stage = 1;
+        else if (stage == 1) f = v % SF_FLOORS, stage = 2;
+        else if (stage == 2) r = v % SF_ROWS, stage = 3;
+        else {
+            const int cell = sf_cell_of(f, r, v % SF_COLS);
+            stage = 1;
+            if (sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT) {
+                sf_init_human(d, env, k.players[i], i, cell, false, k.teams[i], true);
+                SF_AT(d.h_pw, i) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
+                SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)i);
+                ++i, stage = 0;
+            }
+        }
+    }
+}
+
 /* setup() + load_data() + _srand, gameplay.hpp:1231-1277, 1741-1747, 1861-1920; the harness
  * then does "++frame" (play(), :1441) */
 SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
@@ -1279,7 +1306,7 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
     e.mp[1] = 0;
     if (k.mode == SF_MODE_SQUAD) {
         int c0 = sf_cell_of(0, 3, 1);
-        sf_init_human(d, env, k.player, 0, c0, false, 1, true);
+        sf_init_human(d, env, k.players[0], 0, c0, false, 1, true);
         SF_G(c0) = (uint16_t)(C_S0 | 0u);
         for (int i = 1; i < 10; ++i) {
             int c = i < 5 ? sf_cell_of(0, 1, i + 1) : sf_cell_of(2, 1, i + 1);
@@ -1294,29 +1321,14 @@ SF_FN void sf_reset_env(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         e.hw_h = k.n_players;
     } else {
         int c0 = sf_cell_of(0, 1, 1);
-        sf_init_human(d, env, k.player, 0, c0, false, 1, true);
+        sf_init_human(d, env, k.players[0], 0, c0, false, 1, true);
         SF_G(c0) = (uint16_t)(C_S0 | 0u);
         e.mh = 1ull;
         e.hw_h = 1;
     }
     /* the stream of this episode was seeded as the pending one; the next episode's follows */
     sf_install_stream(d, t, env, e, sf_synth_tb(ge), sf_synth_serial(ge, (int64_t)e.episode + 1));
-    if (k.mode == SF_MODE_ROYALE) {
-        /* load_data(), online branch (gameplay.hpp:1847-1859): in index order every player draws
-           way = rand() % 4 + 1, then cells until one prints '.' */
-        for (int i = 0; i < k.n_players; ++i) {
-            const int way0 = sf_rand(e, t) % 4;
-            int cell;
-            for (;;) {
-                const int f = sf_rand(e, t) % SF_FLOORS, r = sf_rand(e, t) % SF_ROWS, c = sf_rand(e, t) % SF_COLS;
-                cell = sf_cell_of(f, r, c);
-                if (sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT) break;
-            }
-            sf_init_human(d, env, k.player, i, cell, false, k.teams[i], true);
-            SF_AT(d.h_pw, i) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
-            SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)i);
-        }
-    }
+    if (k.mode == SF_MODE_ROYALE) sf_royale_place(d, k, t, env, e);
 }
 
 /* ------------------------------------------------------------------ the step */

@@ -186,21 +186,25 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
         if (cfg.throwables[i].range < 1 || cfg.throwables[i].range > 255) return "throwable range must be 1..255";
     for (int i = 0; i < 8; ++i)
         if (cfg.weapons[i].range < 1 || cfg.weapons[i].range > 255) return "weapon range must be 1..255";
-    for (int i = 11; i < 15; ++i)
-        if (cfg.player_sheet[i] < 0 || cfg.player_sheet[i] > 255 || cfg.npc_sheet[i] < 0 || cfg.npc_sheet[i] > 255)
-            return "consumable counts must be 0..255";
-    for (int i = 0; i < 4; ++i)
-        if (cfg.player_sheet[16 + 2 * i] < 0 || cfg.player_sheet[16 + 2 * i] > 255 || cfg.npc_sheet[16 + 2 * i] < 0 ||
-            cfg.npc_sheet[16 + 2 * i] > 255)
-            return "throwable counts must be 0..255";
-    for (int i = 3; i < 6; ++i)
-        if (cfg.player_sheet[i] < 1 || cfg.npc_sheet[i] < 1 || cfg.player_sheet[i] > 400 || cfg.npc_sheet[i] > 400)
-            return "sheet levels must be 1..400";
-    build_template(k.player, cfg.player_sheet, cfg);
+    auto sheet_error = [](const int32_t *sh) -> const char * {
+        for (int i = 11; i < 15; ++i)
+            if (sh[i] < 0 || sh[i] > 255) return "consumable counts must be 0..255";
+        for (int i = 0; i < 4; ++i)
+            if (sh[16 + 2 * i] < 0 || sh[16 + 2 * i] > 255) return "throwable counts must be 0..255";
+        for (int i = 3; i < 6; ++i)
+            if (sh[i] < 1 || sh[i] > 400) return "sheet levels must be 1..400";
+        return nullptr;
+    };
+    if (const char *e = sheet_error(cfg.npc_sheet)) return e;
+    for (int p = 0; p < k.n_players; ++p) {
+        const int32_t *sh = p == 0 ? cfg.player_sheet : cfg.royale_sheets[p];
+        if (const char *e = sheet_error(sh)) return e;
+        build_template(k.players[p], sh, cfg);
+        if (k.players[p].blocks > 255 || k.players[p].portals > 255) return "block / portal allowance above 255";
+        k.player_punch_base[p] = compute_damage(k.players[p].mindamage_def, 1);
+    }
     build_template(k.npc, cfg.npc_sheet, cfg);
-    if (k.player.blocks > 255 || k.player.portals > 255 || k.npc.blocks > 255 || k.npc.portals > 255)
-        return "block / portal allowance above 255";
-    k.player_punch_base = compute_damage(k.player.mindamage_def, 1);
+    if (k.npc.blocks > 255 || k.npc.portals > 255) return "block / portal allowance above 255";
     for (int L = 1; L <= SF_MAX_LEVEL; ++L) { /* gen_human: 3 level-ups per level, Character.hpp:883-887 */
         k.npc_mindamage_def[L] = k.npc.mindamage_def + 15 * (L - 1);
         k.npc_punch_base[L] = compute_damage(k.npc_mindamage_def[L], 1);

@@ -129,8 +129,8 @@ typedef struct SfConst {
     int32_t n_static_exits;
     uint16_t static_exit_cell[SF_MAX_STATIC_EXITS];
     sf_consumable cons[4];
-    SfTemplate player, npc;
-    int32_t player_punch_base;              /* compute_damage(mindamage_def, 1), Character.hpp:393 */
+    SfTemplate players[SF_MAX_PLAYERS], npc; /* [0] = `me`; [1..] only in Battle Royale */
+    int32_t player_punch_base[SF_MAX_PLAYERS]; /* compute_damage(mindamage_def, 1), Character.hpp:393 */
     int32_t npc_punch_base[SF_MAX_LEVEL + 1]; /* per level: gen_human's level-ups, :883-887 */
     int32_t npc_mindamage_def[SF_MAX_LEVEL + 1];
 } SfConst;

@@ -69,21 +69,23 @@ def write(path, tb, serial, sheet, commands, name="1", players=1, ind=0, team=1)
             f.write(chr(c) + "\n")
 
 
-def write_royale(path, tb, serial, sheet, teams, commands, ind=0):
+def write_royale(path, tb, serial, sheets, teams, commands, ind=0):
     """A Battle Royale match as the reference's replay reader takes it (gameplay.hpp:1762-1806): the
     three tokens of the server line, the seeds, ``players ind team``, the sheet of ``ind``, then sheet
     and team of every other player in slot order; ``commands`` are the symbols in file order -- each
     step the command of ``ind``, then that of every other player alive when human_action runs
-    (ascending slot, :966-986).  Every player carries the same ``sheet`` here."""
-    sheet = np.asarray(sheet, dtype=np.int64)
-    assert sheet.shape == (sfdata.SHEET_LEN,) and 2 <= len(teams)
+    (ascending slot, :966-986).  ``sheets``: one int32[32] sheet per player, or a single sheet for all."""
+    sheets = np.asarray(sheets, dtype=np.int64)
+    if sheets.ndim == 1:
+        sheets = np.tile(sheets, (len(teams), 1))
+    assert sheets.shape == (len(teams), sfdata.SHEET_LEN) and 2 <= len(teams)
     with open(path, "w") as f:
         f.write("127.0.0.1 0 none\n")
         f.write("%d %d\n" % (tb, serial))
         f.write("%d %d %d\n" % (len(teams), ind, teams[ind]))
         for i in [ind] + [j for j in range(len(teams)) if j != ind]:
             f.write("player%d\n" % i)
-            for v in sheet:
+            for v in sheets[i]:
                 f.write("%d\n" % int(v))
             if i != ind:
                 f.write("%d\n" % teams[i])

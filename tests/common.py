@@ -57,4 +57,6 @@ def golden_kwargs(g):
     if "teams" in g:
         kw["teams"] = [int(t) for t in g["teams"]]
         kw["caps"] = dict(zip(CAP_KEYS, (int(c) for c in g["caps"])))
+        if "sheets" in g:
+            kw["sheets"] = [str(n) for n in g["sheets"]]
     return kw

@@ -36,6 +36,9 @@ CASES = [
     ("royale_4p_2teams", [1, 2, 2, 1], 1700000777, 31337, 2500, "account1"),
     ("royale_2p_newplayer_a", [1, 2], 1700000003, 1015, 8000, "new_player"),
     ("royale_3p_newplayer_b", [1, 2, 2], 1700000002, 2002, 8000, "new_player"),
+    # every player with a sheet of its own, as announced over the wire (get_info, gameplay.hpp:131-149)
+    ("royale_6p_mixed_sheets", [1, 2, 3, 1, 2, 3], 1700000003, 3003, 3000,
+     ["account1", "new_player", "synthetic", "new_player", "account1", "synthetic"]),
 ]
 
 
@@ -44,12 +47,13 @@ def main(which):
     player of team 3 in the match before would hand that team to the NPC spawned into it."""
     arena = sfdata.load_default()
     for name, teams, tb, serial, steps, player in [CASES[which]]:
-        sheet = arena.player_sheet(player)
+        names = player if isinstance(player, list) else [player] * len(teams)
+        sheet = np.stack([arena.player_sheet(n) for n in names])
         P = len(teams)
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         table = np.frombuffer(bytes(sfcfg.ACTIONS28), dtype=np.uint8)
         actions = table[rng.integers(len(table), size=(steps, P))]
-        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS, player=player)
+        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS, sheets=names)
         o = sfo.Arena(cfg)
         o.reset(1, tb, serial)
         file_cmds = bytearray()
@@ -89,7 +93,7 @@ def main(which):
         actions = actions[:len(status)]
         assert o.status() == status[-1] and np.uint64(o.state_hash()) == hashes[-1] or status[-1] in (5, 6)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), mode=sfcfg.MODE_ROYALE, level=1, tb=tb, serial=serial,
-                            squad_agents=0, player=player, teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
+                            squad_agents=0, player=names[0], sheets=np.array(names), teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
                             actions=actions, status=status, hashes=hashes, records=np.concatenate(records),
                             rec_len=np.array([len(r) for r in records], dtype=np.int64), rec_steps=np.array(rec_steps),
                             obs=np.stack(obs), obs_last=np.stack(obs_last), obs_steps=np.array(obs_steps),

@@ -47,7 +47,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(sfcfg.StepOut) == 32
     assert sfcfg.SfConfig.map_cells.offset % 8 == 0
     assert sfcfg.SfConfig.royale_players.offset == sfcfg.SfConfig.npc_sheet.offset + 4 * sfcfg.SHEET_LEN
-    assert C.sizeof(sfcfg.SfConfig) == sfcfg.SfConfig.royale_teams.offset + 4 * sfcfg.MAX_PLAYERS + 4  # tail padding to 8
+    assert sfcfg.SfConfig.royale_sheets.offset == sfcfg.SfConfig.royale_teams.offset + 4 * sfcfg.MAX_PLAYERS
+    assert C.sizeof(sfcfg.SfConfig) == sfcfg.SfConfig.royale_sheets.offset + 4 * sfcfg.MAX_PLAYERS * sfcfg.SHEET_LEN + 4  # tail padding to 8
 
 
 def test_default_arena_and_reference_parser(arena_data, tmp_path):

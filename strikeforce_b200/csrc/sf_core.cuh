@@ -22,11 +22,13 @@
 #define SF_COLD __device__ __noinline__ /* rare paths stay out of the step kernel's hot code */
 #define SF_MFN __device__ __forceinline__
 #define SF_UNROLL _Pragma("unroll")
+#define SF_NO_UNROLL _Pragma("unroll 1") /* cold loops: the step kernel is instruction-fetch sensitive */
 #else
 #define SF_FN static inline
 #define SF_COLD static
 #define SF_MFN inline
 #define SF_UNROLL
+#define SF_NO_UNROLL
 #endif
 
 /* Warp-lockstep helpers.  The device runs one arena per lane; every loop of the tick has a
@@ -282,6 +284,7 @@ SF_FN void sf_warm_draw(const SfTabs &t, uint32_t Lp[9], const uint32_t c[18], u
 SF_FN void sf_seed_pending(const SfDev &d, const SfTabs &t, int env, int bank, int64_t tb, int64_t u_s)
 {
     uint32_t fast = (tb < 10000000000ll && u_s < 10000000000ll) ? 1u : 0u;
+    SF_NO_UNROLL
     for (int i = 0; i < 18; ++i) {
         uint32_t us = (uint32_t)(u_s % 10 + 1), sd = (uint32_t)(tb % 10 + 1);
         u_s /= 10;
@@ -305,6 +308,7 @@ SF_FN void sf_advance_pending(const SfDev &d, const SfTabs &t, int env, bool val
         for (int j = 0; j < 9; ++j) Lp[j] = SF_AT(d.pend_log, j);
         SF_UNROLL
         for (int i = 0; i < 18; ++i) c[i] = d.rng_cst[sf_cst_index(d, bank, i, env)];
+        SF_NO_UNROLL
         for (int j = 0; j < budget; ++j) {
             if (n < SF_WARM_DRAWS) {
                 sf_warm_draw(t, Lp, c, n);
@@ -405,30 +409,35 @@ SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, u
     SF_G(cell) = (uint16_t)(g | C_S2);
 }
 
-/* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469), -1 if none */
-SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
+/* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469), -1 if none.
+ * A rare event (a stale or missing hint, sf_built_slot), called from several places: one
+ * out-of-line copy that takes plain values, so the arena's registers stay where they are. */
+SF_FN int sf_find_built_in(const uint16_t *tc, uint32_t ntemp, int cell)
 {
     int found = -1;
-    const uint16_t *tc = &SF_T(d.t_cell, 0);
 #ifdef __CUDA_ARCH__
     /* the per-arena record block is 16-byte aligned (cap_t is a multiple of 8) */
     const uint4 *tv = reinterpret_cast<const uint4 *>(tc);
     const uint32_t want = (uint32_t)cell;
-    /* callers are rare events inside divergent code, so the walk may stop at the first hit */
-    for (uint32_t q0 = 0; q0 < e.ntemp && found < 0; q0 += 8) {
+    /* callers are inside divergent code, so the walk may stop at the first hit */
+    for (uint32_t q0 = 0; q0 < ntemp && found < 0; q0 += 8) {
         uint4 v = tv[q0 >> 3];
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
         SF_UNROLL
         for (int j = 3; j >= 0; --j) {
-            if ((w[j] >> 16) == want && q0 + 2 * j + 1 < e.ntemp) found = (int)(q0 + 2 * j + 1);
-            if ((w[j] & 0xFFFFu) == want && q0 + 2 * j < e.ntemp) found = (int)(q0 + 2 * j);
+            if ((w[j] >> 16) == want && q0 + 2 * j + 1 < ntemp) found = (int)(q0 + 2 * j + 1);
+            if ((w[j] & 0xFFFFu) == want && q0 + 2 * j < ntemp) found = (int)(q0 + 2 * j);
         }
     }
 #else
-    for (uint32_t q = 0; q < e.ntemp && found < 0; ++q)
+    for (uint32_t q = 0; q < ntemp && found < 0; ++q)
         if (tc[q] == cell) found = (int)q;
 #endif
     return found;
+}
+SF_FN int sf_find_built(const SfDev &d, int env, const SfEnv &e, int cell)
+{
+    return sf_find_built_in(&SF_T(d.t_cell, 0), e.ntemp, cell);
 }
 /* A player-built cell that nobody stands on carries a HINT of its record's slot in the bits the
  * occupant does not need (0-7 and 14-15, ten bits).  The hint is always validated against the

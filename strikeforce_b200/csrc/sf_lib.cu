@@ -88,9 +88,19 @@ sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *
     sf_stage_tables(d, t);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = d.E >> 5;
+#ifndef SF_NO_PHASE_BARRIERS
+    /* every warp of the CTA makes the same number of passes (a pass without a chunk walks through
+       with all lanes off), so that the phase barriers of sf_step_halves line up */
+    const int per_pass = gridDim.x * (SF_CTA / 32);
+    for (int base = 0; base < nchunks; base += per_pass) {
+        const int chunk = base + blockIdx.x + gridDim.x * warp;
+        int env = chunk < nchunks ? chunk * 32 + lane : lane;
+        bool valid = chunk < nchunks && env < d.n_envs;
+#else
     for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
         int env = chunk * 32 + lane;
         bool valid = env < d.n_envs;
+#endif
         SfStatDelta sd;
         memset(&sd, 0, sizeof sd);
         sf_step_body(d, k, t, env, valid, (actions && valid) ? actions + (size_t)env * k.n_agents : nullptr, HALF, sd);

@@ -53,25 +53,6 @@
 #define SF_PHASE_SYNC() ((void)0)
 #endif
 
-/* Experiment: loops with a CTA-uniform trip count and a barrier per round (the phase barrier makes a
- * warp wait for the slowest warp of its CTA anyway). */
-#if defined(__CUDA_ARCH__) && defined(SF_ROUND_BARRIERS) && !defined(SF_NO_PHASE_BARRIERS)
-__device__ __forceinline__ int sf_cta_max(int warp_max)
-{
-    __shared__ int s;
-    if (threadIdx.x == 0) s = -2147483647;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) atomicMax(&s, warp_max);
-    __syncthreads();
-    return s;
-}
-#define SF_LOOP_MAX(x) sf_cta_max(SF_WARP_MAX(x))
-#define SF_ROUND_SYNC() __syncthreads()
-#else
-#define SF_LOOP_MAX(x) SF_WARP_MAX(x)
-#define SF_ROUND_SYNC() ((void)0)
-#endif
-
 #define SF_RNG_ZERO 0x10000u /* log-domain marker of the value 0 (only during the warm-up) */
 
 /* tables every lane reads: shared memory on the device, plain arrays in the host check */
@@ -571,7 +552,7 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
                 }
             }
         }
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
 }
 
@@ -583,7 +564,7 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
  * zombie's loaded copy so that it sees exactly what a sequential walk would. */
 SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
-    const int hi = SF_LOOP_MAX(e.on ? m2_highest(e.mz) : -1);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mz) : -1);
     /* zombies neither appear nor vanish here: liveness comes from a snapshot of the mask, and the
      * positions of a round are loaded one round ahead */
     const uint64_t live0 = e.on ? e.mz[0] : 0ull, live1 = e.on ? e.mz[1] : 0ull;
@@ -684,7 +665,7 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                 }
             }
         }
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
 }
 
@@ -697,7 +678,7 @@ SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
      * one); an arena whose flag is down reads none of its exits, and the flag comes down again
      * when a pass finds every exit free */
     const bool look = e.on && e.watch;
-    const int hi = SF_LOOP_MAX(look ? m2_highest(e.mp) : -1);
+    const int hi = SF_WARP_MAX(look ? m2_highest(e.mp) : -1);
     bool any = false;
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
@@ -720,7 +701,7 @@ SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
                 }
             }
         }
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
     if (look) e.watch = any;
 }
@@ -833,7 +814,7 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
     const bool built_any = e.ntemp != 0;
     int hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0; /* cells that absorbed a bullet in this call */
     int n_hit = 0;
-    const int hi = SF_LOOP_MAX(e.on ? m2_highest(e.mb) : -1);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
     /* liveness is tested against a snapshot of the mask (every slot is visited once), and the
      * flags / positions of a round are loaded one round ahead, so that they are in flight
      * together with the cell loads of the round before */
@@ -895,7 +876,7 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
                 }
             }
         }
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
     /* a limit can only be crossed by an absorption of this very call (while a human hides an
      * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
@@ -932,7 +913,7 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
  * ahead, load together); a newly set s[2] is forwarded to the later bullets of the round. */
 SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
 {
-    const int hi = SF_LOOP_MAX(e.on ? m2_highest(e.mb) : -1);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
     int r = 0;
     if (e.on) r = sf_rand(e, t) & 1;
     SF_SYNCWARP();
@@ -999,7 +980,7 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
                 }
             }
         }
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
     if (oob) sf_fail_env(e, SF_UB_GUARD);
 }
@@ -1240,7 +1221,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
 {
     /* commands wait in h_cmd between the two loops (command[], gameplay.hpp:43) */
     const uint64_t live = e.on ? e.mh : 0ull;
-    const int hi = SF_LOOP_MAX(live ? sf_fls64(live) : -1);
+    const int hi = SF_WARP_MAX(live ? sf_fls64(live) : -1);
     const int cmd0 = (actions && e.on) ? actions[0] : '+';
     for (int h = 1; h <= hi; ++h) {
         bool is_live = (live >> h) & 1;
@@ -1258,7 +1239,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
             }
         }
         if (is_live) SF_AT(d.h_cmd, h) = (uint8_t)c;
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
     int r = 0;
     if (e.on) r = sf_rand(e, t) & 1;
@@ -1281,7 +1262,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
                 pw_n = SF_AT(d.h_pw, hn), sel_n = SF_AT(d.h_sel, hn), c_n = hn == 0 ? cmd0 : (int)SF_AT(d.h_cmd, hn);
         }
         if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, c, pw, sel);
-        SF_SYNCWARP(); SF_ROUND_SYNC();
+        SF_SYNCWARP();
     }
 }
 

@@ -20,25 +20,30 @@ from strikeforce_b200.sim import BatchedArena  # noqa: E402
 
 arena = sfdata.load_default()
 FULL = sfcfg.ACTIONS28 + b"_3" + b"12p~ \x00\xff"
-CASES = [  # mode, level range, envs, steps, table, agents, player, caps, max_steps
+ROYALE_CAPS = dict(cap_portals=128, cap_built=1000, cap_bullets=128)
+CASES = [  # mode, level range, envs, steps, table, agents, player, caps, max_steps (Battle Royale: 16 players, 4 teams)
     (sfcfg.MODE_SOLO, (1, 3), 48, 3000, FULL, False, "account1", None, 1500),
     (sfcfg.MODE_TIMER, (1, 2), 32, 2500, sfcfg.ACTIONS28, False, "synthetic", None, 0),
     (sfcfg.MODE_SQUAD, (1, 10), 48, 3000, FULL, False, "account1", None, 2048),
     (sfcfg.MODE_SQUAD, (2, 4), 32, 2000, sfcfg.ACTIONS9, True, "account1", None, 1000),
     (sfcfg.MODE_SOLO, (1, 1), 48, 2500, sfcfg.ACTIONS28, False, "account1",
      dict(cap_humans=16, cap_zombies=24, cap_bullets=12, cap_built=24, cap_portals=12), 0),
+    (sfcfg.MODE_ROYALE, (1, 1), 40, 2500, FULL, False, "account1", ROYALE_CAPS, 1200),
+    (sfcfg.MODE_ROYALE, (1, 1), 40, 4000, sfcfg.ACTIONS28, False, "new_player", ROYALE_CAPS, 0),
 ]
+TEAMS = [1, 2, 3, 4] * 4
 t00 = time.time()
 for mode, (l0, l1), n, steps, table, agents, player, caps, max_steps in CASES:
     base = 777
+    teams = TEAMS if mode == sfcfg.MODE_ROYALE else None
     sim = BatchedArena(n, mode=mode, level=l0, level_max=l1, squad_agents=agents, auto_reset=True, max_steps=max_steps,
-                       env_id_base=base, player=player, caps=caps)
+                       env_id_base=base, player=player, caps=caps, teams=teams)
     span = l1 - l0 + 1
     oracles, levels = [], []
     for e in range(n):
         lvl = l0 + (base + e) % span
         cfg = sfcfg.make_config(arena, mode=mode, level_min=lvl, squad_agents=agents, max_steps=max_steps, player=player,
-                                caps=caps)
+                                caps=caps, teams=teams)
         o = sfo.Arena(cfg)
         o.reset(lvl, common.synth_tb(base + e), common.synth_serial(base + e, 0))
         oracles.append(o)

@@ -47,10 +47,13 @@
  * code: the step kernel is ~210 KB of SASS and 13% of its stall samples were instruction fetch;
  * with the barriers a step is 3% shorter (callers: only the step kernels, whose warps all make the
  * same number of passes). */
+#ifndef SF_BARRIER_MASK
+#define SF_BARRIER_MASK 0x1F
+#endif
 #if defined(__CUDA_ARCH__) && !defined(SF_NO_PHASE_BARRIERS)
-#define SF_PHASE_SYNC() __syncthreads()
+#define SF_PHASE_SYNC(n) do { if ((SF_BARRIER_MASK >> (n)) & 1) __syncthreads(); } while (0)
 #else
-#define SF_PHASE_SYNC() ((void)0)
+#define SF_PHASE_SYNC(n) ((void)0)
 #endif
 
 #define SF_RNG_ZERO 0x10000u /* log-domain marker of the value 0 (only during the warm-up) */
@@ -1400,20 +1403,20 @@ SF_FN void sf_step_halves(const SfDev &d, const SfConst &k, const SfTabs &t, int
 {
 #pragma unroll 1
     for (int ph = first; ph <= last; ++ph) {
-        SF_PHASE_SYNC();
+        SF_PHASE_SYNC(0);
         if (ph == 0) {
             sf_spawns(d, k, t, env, e);
-            SF_PHASE_SYNC();
+            SF_PHASE_SYNC(1);
             sf_zombie_action(d, k, t, env, e);
-            SF_PHASE_SYNC();
+            SF_PHASE_SYNC(2);
             sf_portal_damage(d, k, env, e);
         } else {
             sf_human_action(d, k, t, env, e, actions);
         }
-        SF_PHASE_SYNC();
+        SF_PHASE_SYNC(3);
         sf_resolve_bullets(d, k, env, e);
         if (e.on) e.frame += 1;
-        SF_PHASE_SYNC();
+        SF_PHASE_SYNC(4);
         sf_update_bull(d, t, env, e);
     }
     if (last == 1) {

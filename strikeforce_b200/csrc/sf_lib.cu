@@ -483,7 +483,7 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     }
     if (smem_optin < SF_SMEM_BYTES) {
         delete h;
-        return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 140,080 B)");
+        return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 141,056 B)");
     }
     Carver sizer;
     carve(sizer, *h);

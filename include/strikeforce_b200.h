@@ -157,11 +157,12 @@ int sf_step(sf_handle *h, const uint8_t *actions, void *stream);
 int sf_step_a(sf_handle *h, void *stream);
 int sf_step_b(sf_handle *h, const uint8_t *actions, void *stream);
 
-/* The same step through HOST buffers (the call a CPU-side trainer makes): copies
-   actions host->device, steps, delivers sf_step_out[n_envs] to out_host and synchronises.
-   If out_host is page-locked (cudaHostAlloc / cudaHostRegister) the kernel stores each arena's
-   result straight into it while the other arenas are still stepping; a pageable buffer gets a
-   device->host copy after the step. */
+/* The same step through HOST buffers (the call a CPU-side trainer makes): takes the actions from
+   actions_host, steps, delivers sf_step_out[n_envs] to out_host and synchronises.
+   Page-locked buffers (cudaHostAlloc / cudaHostRegister) are used in place: the kernel reads each
+   arena's commands from actions_host when human_action needs them and stores each arena's result
+   into out_host while the other arenas are still stepping.  Pageable buffers are copied (host->device
+   before, device->host after the step). */
 int sf_step_host(sf_handle *h, const uint8_t *actions_host, sf_step_out *out_host, void *stream);
 
 /* Fill a device action buffer with the synthetic stream of sf_synth.h for global step t. */

@@ -606,17 +606,24 @@ int sf_step_host(sf_handle *h, const uint8_t *actions_host, sf_step_out *out_hos
     if (!h || !actions_host || !out_host) return h ? sf_fail(h, SF_ERR_ARG, "sf_step_host: null argument") : SF_ERR_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     size_t na = (size_t)h->d.n_envs * (size_t)h->k.n_agents;
-    SF_CUDA(h, cudaMemcpyAsync(h->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
-    /* a pinned (cudaHostAlloc / cudaHostRegister) result buffer is written by the kernel itself as
-       each warp finishes its arenas, so the transfer overlaps the step; a pageable one gets a copy */
-    sf_step_out *mirror = nullptr;
-    cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
-        mirror = static_cast<sf_step_out *>(pa.devicePointer);
-    else
+    /* page-locked buffers (cudaHostAlloc / cudaHostRegister) are used in place: the kernel reads each
+       arena's commands from the action buffer when human_action needs them and stores each arena's
+       result as its warp finishes, so both transfers overlap the step; pageable ones are copied */
+    auto device_view = [](const void *p) -> void * {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            return pa.devicePointer;
         cudaGetLastError();
+        return nullptr;
+    };
+    const uint8_t *actions = static_cast<const uint8_t *>(device_view(actions_host));
+    if (!actions) {
+        SF_CUDA(h, cudaMemcpyAsync(h->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
+        actions = h->d_actions;
+    }
+    sf_step_out *mirror = static_cast<sf_step_out *>(device_view(out_host));
     h->d.out_mirror = mirror;
-    int rc = sf_launch_step(h, SF_HALF_BOTH, h->d_actions, s);
+    int rc = sf_launch_step(h, SF_HALF_BOTH, actions, s);
     h->d.out_mirror = nullptr;
     if (rc) return rc;
     if (!mirror)

@@ -137,7 +137,8 @@ def test_step_host_matches_device_step(torch_cuda, arena_data, pinned):
         for t in range(120):  # crosses two auto-resets
             act = a.synth_actions(t)
             a.step(act)
-            b.step_host(act.cpu().numpy(), out_h)
+            act_h = act.cpu().pin_memory() if pinned else act.cpu()  # page-locked buffers are used in place
+            b.step_host(act_h.numpy(), out_h)
             out_d = a.step_out().cpu().numpy()
             assert (out_d == out_h.view(np.int32).reshape(64, 8)).all()
         assert (a.state_hash() == b.state_hash()).all()

@@ -1,0 +1,162 @@
+"""Match-server bridge -- STARTED, parity unpinned.
+
+The reference's match server (StrikeForce-server/server.cpp) only relays: it accepts ``n`` players,
+tells everyone the seeds and the roster, and then, tick by tick, collects one command byte from every
+live player and sends each player the bytes of the others; every client steps its own copy of the
+match, which stays identical because the tick is deterministic (client side: gameplay.hpp:66-193).
+``MatchHost`` speaks that protocol and can additionally fill seats itself (``local_seats``: players
+whose commands come from the host, e.g. device-side agents) and hand every tick's command row to an
+arena of its own (``BatchedArena`` in Battle Royale mode) -- a GPU-hosted match that stock clients
+can join, because the device tick is bit-exact.
+
+Wire format, all messages NUL-terminated (server.cpp):
+  :199-213  client -> password; server -> "A" or "R"
+  :229-236  server -> "<tb> <serial>", then "<n> <index> <team>"
+  :237-250  every client -> its character sheet (the text of its account file); the server relays it
+            to every other client followed by "<team>"
+  :62-117   per tick: every live client -> one command byte ('_' quit, '~' eliminated);
+            server -> to every live client the bytes of all other live players, in index order
+            (plus, once, the '_' of a player that just quit)
+  :108-132  the match ends when the live players' teams no longer change along the index order
+
+Not pinned yet against the reference's own client code (planned: oracle/ref_harness, one process per
+player); the tests drive it with scripted socket clients and check the bytes and the arena.
+"""
+from __future__ import annotations
+
+import socket
+
+
+def recv_cstr(sock, limit=4096):
+    """my_recv, server.cpp:62-75: bytes up to the terminating NUL; None when the peer is gone."""
+    out = bytearray()
+    while len(out) < limit:
+        try:
+            b = sock.recv(1)
+        except OSError:
+            return None
+        if not b:
+            return None
+        if b == b"\0":
+            return bytes(out)
+        out += b
+    return bytes(out)
+
+
+def send_cstr(sock, payload: bytes):
+    sock.sendall(payload + b"\0")
+
+
+class MatchHost:
+    """One match.  ``teams[i]`` = team of seat i; ``local_seats`` = {seat: sheet text} for the seats the
+    host plays itself; the other seats are taken by connecting clients in the order they connect."""
+
+    def __init__(self, teams, password, tb, serial, local_seats=None):
+        self.teams = list(teams)
+        self.n = len(self.teams)
+        self.password = password.encode() if isinstance(password, str) else bytes(password)
+        self.tb, self.serial = int(tb), int(serial)
+        self.local = dict(local_seats or {})
+        self.socks = {}  # seat -> socket of a remote player
+        self.alive = [True] * self.n
+        self.announce = [False] * self.n
+        self.command = [ord("+")] * self.n
+        self.sheets = {}  # seat -> the sheet text every player announced
+
+    # ---------------------------------------------------------------- lobby, server.cpp:196-250
+    @property
+    def remote_seats(self):
+        return [i for i in range(self.n) if i not in self.local]
+
+    def accept(self, listener):
+        """Fill the remote seats; a wrong password gets "R" and does not take a seat."""
+        for seat in self.remote_seats:
+            while seat not in self.socks:
+                conn, _ = listener.accept()
+                conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                pw = recv_cstr(conn, 32)
+                if pw == self.password:
+                    send_cstr(conn, b"A")
+                    self.socks[seat] = conn
+                else:
+                    send_cstr(conn, b"R")
+                    conn.close()
+
+    def handshake(self):
+        for s in self.socks.values():
+            send_cstr(s, b"%d %d" % (self.tb, self.serial))
+        for i, s in self.socks.items():
+            send_cstr(s, b"%d %d %d" % (self.n, i, self.teams[i]))
+        for i in range(self.n):
+            info = self.local[i].encode() if i in self.local else (recv_cstr(self.socks[i], 2048) or b"")
+            self.sheets[i] = info.decode("latin-1")
+            for j, s in self.socks.items():
+                if j != i:
+                    send_cstr(s, info)
+                    send_cstr(s, b"%d" % self.teams[i])
+
+    # ---------------------------------------------------------------- one tick, server.cpp:77-132
+    def tick(self, local_commands=None):
+        """Collect, relay, judge.  ``local_commands``: {seat: command byte} for the host's own seats
+        ('~' when the arena says that player is dead).  Returns (command row for the arena, winner)."""
+        local_commands = local_commands or {}
+        for i in range(self.n):
+            if not self.alive[i]:
+                continue
+            if i in self.local:
+                c = int(local_commands.get(i, ord("+")))
+                gone = False
+            else:
+                msg = recv_cstr(self.socks[i], 2)
+                gone = msg is None
+                c = ord("_") if gone else (msg[0] if msg else 0)
+            self.command[i] = c
+            if c in (ord("_"), ord("~")) or gone:
+                self.alive[i] = False
+                if i in self.socks:
+                    self.socks[i].close()
+                if c == ord("_"):
+                    self.announce[i] = True
+        for i, s in self.socks.items():
+            if self.alive[i]:
+                for j in range(self.n):
+                    if (self.alive[j] or self.announce[j]) and i != j:
+                        s.sendall(bytes([self.command[j], 0]))
+        row = bytes(self.command[i] if (self.alive[i] or self.announce[i] or self.command[i] == ord("~")) else ord("+")
+                    for i in range(self.n))
+        return row, self._result()
+
+    def _result(self):
+        """result(), server.cpp:108-132, quirk included: it counts team CHANGES along the index order."""
+        winner = num = 0
+        self.live_count = 0
+        for i in range(self.n):
+            if self.alive[i]:
+                if self.teams[i] != winner:
+                    num, winner = num + 1, self.teams[i]
+                self.live_count += 1
+            else:
+                self.announce[i] = False
+        return winner if num == 1 else 0
+
+    def close(self):
+        for s in self.socks.values():
+            try:
+                s.close()
+            except OSError:
+                pass
+
+
+def host_match(host: MatchHost, step, local_policy=None, max_ticks=1 << 30):
+    """The server's main loop (server.cpp:268-272) with an arena attached: ``step(row)`` advances
+    the host's arena by one env-step with one command per seat; ``local_policy(seat)`` returns the
+    command byte of a host-played seat.  Returns (winner, ticks)."""
+    winner, ticks = 0, 0
+    while not winner and ticks < max_ticks:
+        cmds = {i: local_policy(i) for i in host.local if host.alive[i]} if local_policy else {}
+        row, winner = host.tick(cmds)
+        step(row)
+        ticks += 1
+        if not host.live_count:
+            break
+    return winner, ticks

@@ -375,3 +375,58 @@ def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):
             assert stats["steps"] + stats["overflows"] + stats["ub_guards"] == 96 * 12
         finally:
             sim.close()
+
+
+def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
+    """a match hosted with the reference server's wire protocol
+    (strikeforce_b200.match_server) whose authoritative arena lives on the GPU; two scripted socket
+    clients and one host-played seat, the arena compared with the oracle fed the relayed commands."""
+    import socket
+    import threading
+    import time
+    import test_match_server as tms
+    from strikeforce_b200 import match_server as ms
+    from strikeforce_b200.sim import BatchedArena
+    torch = torch_cuda
+    teams, tb, serial, T = [1, 2, 1], 1700000321, 777, 40
+    sheet = "p\n" + "\n".join(str(int(v)) for v in arena_data.player_sheet("account1"))
+    acts = np.stack([common.synth_actions([9], 3, t, sfcfg.ACTIONS28)[0] for t in range(T)])
+    listener = socket.socket()
+    listener.bind(("127.0.0.1", 0))
+    listener.listen(4)
+    port = listener.getsockname()[1]
+    host = ms.MatchHost(teams, "pw", tb, serial, local_seats={1: sheet})
+    lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
+    lobby.start()
+    clients = []
+    for seat in (0, 2):
+        c = tms.ScriptedClient(port, b"pw", sheet, [(int(acts[t, seat]), set()) for t in range(T)])
+        c.start()
+        clients.append(c)
+        time.sleep(0.2)
+    lobby.join(20)
+    host.handshake()
+    sim = BatchedArena(1, mode="Royale", teams=teams, auto_reset=False)
+    cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False)
+    o = sfo.Arena(cfg)
+    o.reset(1, tb, serial)
+    try:
+        sim.reset([0], [tb], [serial])
+        tick = [0]
+
+        def step(row):
+            sim.step(torch.tensor(list(row), dtype=torch.uint8, device=sim.device).view(1, 3))
+            o.step(row)
+
+        def policy(seat):
+            tick[0] += 1
+            return int(acts[tick[0] - 1, 1])
+
+        winner, ticks = ms.host_match(host, step, policy, max_ticks=T)
+        assert ticks == T and winner == 0
+        assert np.uint64(sim.state_hash()[0].item() & 0xFFFFFFFFFFFFFFFF) == np.uint64(o.state_hash())
+        for c in clients:
+            c.join(10)
+            assert c.error is None and len(c.received) == T
+    finally:
+        sim.close(), host.close(), listener.close()

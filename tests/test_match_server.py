@@ -1,0 +1,125 @@
+"""strikeforce_b200.match_server: the reference match server's wire protocol (StrikeForce-server/
+server.cpp) driven by scripted socket clients that behave like the reference client's network code
+(gameplay.hpp:66-193: start / give_info / get_info / send_it / recieve), with the C oracle standing
+in for the host's arena (on a B200 box that is a BatchedArena in Battle Royale mode)."""
+import socket
+import threading
+
+import numpy as np
+
+import common
+import sfo
+from strikeforce_b200 import config as sfcfg
+from strikeforce_b200 import match_server as ms
+
+
+class ScriptedClient(threading.Thread):
+    """What the reference client does on the wire, with a fixed command script."""
+
+    def __init__(self, port, password, sheet_text, script):
+        super().__init__(daemon=True)
+        self.port, self.password, self.sheet_text, self.script = port, password, sheet_text, script
+        self.accepted = None
+        self.seeds = self.roster = None
+        self.others = []   # (sheet text, team) in the order received
+        self.received = []  # per tick: bytes of the other players
+        self.error = None
+
+    def run(self):
+        try:
+            s = socket.create_connection(("127.0.0.1", self.port))
+            ms.send_cstr(s, self.password)                        # start(), :91
+            self.accepted = ms.recv_cstr(s) == b"A"
+            if not self.accepted:
+                return
+            self.seeds = tuple(int(x) for x in ms.recv_cstr(s).split())    # :101-102
+            n, ind, team = (int(x) for x in ms.recv_cstr(s).split())       # :104-105
+            self.roster = (n, ind, team)
+            ms.send_cstr(s, self.sheet_text.encode())             # give_info(), :120-133
+            live = [True] * n
+            for i in range(n):                                     # get_info(), :135-152
+                if i != ind:
+                    self.others.append((ms.recv_cstr(s).decode(), int(ms.recv_cstr(s))))
+            for c, leaving in self.script:                         # send_it() / recieve(), :113-118, 170-193
+                s.sendall(bytes([c, 0]))
+                if c in (ord("_"), ord("~")):
+                    break
+                got = []
+                for i in leaving:  # dead in this client's own copy of the match (mh[i] false): recieve() skips them
+                    live[i] = False
+                for i in range(n):
+                    if i != ind and live[i]:
+                        b = ms.recv_cstr(s)
+                        got.append(b[0] if b else 0)
+                        if b == b"_":
+                            live[i] = False  # obey('_') zeroes that player's Hp: gone from the next tick on
+                self.received.append(bytes(got))
+            s.close()
+        except Exception as e:  # surfaces in the main thread's asserts
+            self.error = e
+
+
+def test_protocol_roster_relay_quit_and_winner(arena_data):
+    teams, tb, serial, T = [1, 2, 1], 1700000099, 4242, 12
+    sheets = {i: "player%d\n" % i + "\n".join(str(int(v)) for v in arena_data.player_sheet("account1")) for i in range(3)}
+    act = common.synth_actions([5], 3, 0, sfcfg.ACTIONS28)
+    acts = np.stack([common.synth_actions([5], 3, t, sfcfg.ACTIONS28)[0] for t in range(T)])
+    acts[acts == ord("_")] = ord("+")
+    # seat 2 quits at tick 6; the host-played seat 1 is eliminated ('~') at tick 9 -> team 1 wins
+    script0 = [(int(acts[t, 0]), {1} if t == 9 else set()) for t in range(10)]
+    script2 = [(int(acts[t, 2]), set()) for t in range(6)] + [(ord("_"), set())]
+    listener = socket.socket()
+    listener.bind(("127.0.0.1", 0))
+    listener.listen(8)
+    port = listener.getsockname()[1]
+    host = ms.MatchHost(teams, "secret", tb, serial, local_seats={1: sheets[1]})
+    lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
+    lobby.start()
+    intruder = ScriptedClient(port, b"wrong", sheets[0], [])
+    intruder.start()
+    intruder.join(10)
+    c0 = ScriptedClient(port, b"secret", sheets[0], script0)
+    c0.start()
+    import time
+    time.sleep(0.2)  # seat order = connection order
+    c2 = ScriptedClient(port, b"secret", sheets[2], script2)
+    c2.start()
+    lobby.join(10)
+    assert intruder.accepted is False and sorted(host.socks) == [0, 2]
+    host.handshake()
+    # the host's arena: the C oracle here, a BatchedArena("Royale") on the GPU
+    cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False)
+    arena, twin = sfo.Arena(cfg), sfo.Arena(cfg)
+    arena.reset(1, tb, serial), twin.reset(1, tb, serial)
+    rows = []
+
+    def step(row):
+        rows.append(row)
+        arena.step(row)
+
+    tick = [0]
+
+    def local_policy(seat):
+        t = tick[0]
+        tick[0] += 1
+        return ord("~") if t == 9 else int(acts[t, 1])
+
+    winner, ticks = ms.host_match(host, step, local_policy, max_ticks=50)
+    c0.join(10), c2.join(10)
+    assert c0.error is None and c2.error is None, (c0.error, c2.error)
+    # lobby messages
+    assert c0.seeds == (tb, serial) == c2.seeds and c0.roster == (3, 0, 1) and c2.roster == (3, 2, 1)
+    assert c0.others == [(sheets[1], 2), (sheets[2], 1)] and c2.others == [(sheets[0], 1), (sheets[1], 2)]
+    # relay: index order, the quit announced once, nothing for a player that is gone
+    for t in range(6):
+        assert c0.received[t] == bytes([acts[t, 1], acts[t, 2]]) and c2.received[t] == bytes([acts[t, 0], acts[t, 1]])
+    assert c0.received[6] == bytes([acts[6, 1], ord("_")])
+    assert c0.received[7] == bytes([acts[7, 1]]) and c0.received[8] == bytes([acts[8, 1]])
+    assert c0.received[9] == b""  # the eliminated player sends '~' to the server only
+    assert winner == 1 and ticks == 10
+    # the arena saw one command per seat and tick ('_' of the quitter once, then nothing of it)
+    assert rows[6] == bytes([acts[6, 0], acts[6, 1], ord("_")]) and rows[7] == bytes([acts[7, 0], acts[7, 1], ord("+")])
+    for r in rows:
+        twin.step(r)
+    assert arena.state_hash() == twin.state_hash() and len(rows) == 10
+    host.close(), listener.close()

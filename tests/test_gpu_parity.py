@@ -383,7 +383,6 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
     clients and one host-played seat, the arena compared with the oracle fed the relayed commands."""
     import socket
     import threading
-    import time
     import test_match_server as tms
     from strikeforce_b200 import match_server as ms
     from strikeforce_b200.sim import BatchedArena
@@ -403,7 +402,7 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
         c = tms.ScriptedClient(port, b"pw", sheet, [(int(acts[t, seat]), set()) for t in range(T)])
         c.start()
         clients.append(c)
-        time.sleep(0.2)
+        tms.wait_for_seat(host, seat)
     lobby.join(20)
     host.handshake()
     sim = BatchedArena(1, mode="Royale", teams=teams, auto_reset=False)

@@ -59,6 +59,14 @@ class ScriptedClient(threading.Thread):
             self.error = e
 
 
+def wait_for_seat(host, seat, timeout=20.0):
+    import time
+    t0 = time.time()
+    while seat not in host.socks:
+        assert time.time() - t0 < timeout, "no client took seat %d" % seat
+        time.sleep(0.005)
+
+
 def test_protocol_roster_relay_quit_and_winner(arena_data):
     teams, tb, serial, T = [1, 2, 1], 1700000099, 4242, 12
     sheets = {i: "player%d\n" % i + "\n".join(str(int(v)) for v in arena_data.player_sheet("account1")) for i in range(3)}
@@ -80,8 +88,7 @@ def test_protocol_roster_relay_quit_and_winner(arena_data):
     intruder.join(10)
     c0 = ScriptedClient(port, b"secret", sheets[0], script0)
     c0.start()
-    import time
-    time.sleep(0.2)  # seat order = connection order
+    wait_for_seat(host, 0)  # seats are handed out in connection order
     c2 = ScriptedClient(port, b"secret", sheets[2], script2)
     c2.start()
     lobby.join(10)

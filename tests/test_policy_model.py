@@ -88,3 +88,20 @@ def test_policy_agent_is_seeded_and_batched():
     for _ in range(3):
         r1, r2 = a1.predict(x), a2.predict(x)
         assert r1.shape == (4,) and torch.equal(r1, r2) and int(r1.max()) < 9
+
+
+def test_chunked_predict_is_the_same_policy():
+    """PolicyAgent(chunk=...) bounds the activations of very large batches (configs[4]: 524,288
+    observations per tick); rows are independent, so chunking changes neither the sampled actions
+    (same generator order) nor the recurrent state."""
+    import torch
+    from strikeforce_b200 import policy
+    torch.manual_seed(0)
+    m = policy.AgentModel()
+    a = policy.PolicyAgent(m, 10, device="cpu", seed=5)
+    b = policy.PolicyAgent(m, 10, device="cpu", seed=5, chunk=4)
+    x = torch.rand(10, 32, 31, 31)
+    for _ in range(3):
+        assert a.predict(x).tolist() == b.predict(x).tolist()
+        for s, t in zip(a.state, b.state):
+            assert torch.allclose(s, t, atol=1e-6)

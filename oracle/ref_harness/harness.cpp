@@ -224,6 +224,51 @@ int sfref_reset_ex(int mode, int level, const char *player_template, int squad_a
     return 0;
 }
 
+// A LIVE online match (gameplay.hpp:1807-1859): load_data() asks for the server's address, port and
+// password on std::cin, and the reference's own client code (gameplay.hpp:66-193) connects, receives
+// seeds and roster, announces the account sheet of `user` (./accounts/game/<user>/info, <user>.txt in
+// the run directory) and receives the other players'.  Used to pin strikeforce_b200/match_server.py.
+int sfref_reset_online(const char *ip, int port, const char *password, const char *user_name, const int *caps,
+                       long max_steps)
+{
+    if (!g_inited) return -1;
+    if (caps) g_caps = Caps{caps[0], caps[1], caps[2], caps[3], caps[4], caps[5]};
+    else g_caps = Caps{9000, 9000, 9000, 9000, 9000, 9000};
+    g_mode = SF_MODE_ROYALE;
+    g_squad_agents = false;
+    g_max_steps = max_steps;
+    if (g.log_file.is_open()) g.log_file.close();
+    if (g.replay_file.is_open()) g.replay_file.close();
+    user = user_name;
+    g_template = std::string("./accounts/game/") + user_name + "/info, " + user_name + ".txt";
+    ECh::me = ECh::Human();
+    ECh::me.build(false, "", g_template);
+    g.manual = false;
+    g.replay_mode = false;
+    g.enable_logging = false;
+    g.mode = mode_name(SF_MODE_ROYALE);
+    g.level = 1;
+    g.chest = 0;
+    std::streambuf *old_cin = std::cin.rdbuf();
+    std::istringstream fake(std::string(ip) + "\n" + std::to_string(port) + "\n" + password + "\n");
+    std::cin.rdbuf(fake.rdbuf());
+    std::streambuf *old_cout = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    g.setup();
+    std::cin.rdbuf(old_cin);
+    std::cout.rdbuf(old_cout);
+    if (disconnect) return -2;
+    hum[ind].agent->slot = ind;
+    ++g.frame;
+    g_status = SF_RUNNING;
+    g_steps = 0;
+    g_hw_h = 0;
+    std::memset(g_hub.captured, 0, sizeof(g_hub.captured));
+    track_and_check_caps();
+    return ind;
+}
+
 // the seeds of the running match (after a logging reset: the reference's own, as written to the log)
 void sfref_seeds(long long *out) { out[0] = (long long)g.tb; out[1] = (long long)g.serial_number; }
 
@@ -250,6 +295,7 @@ int sfref_step(const unsigned char *actions, int n)
     if (g.frame % g.ph <= 1) g.spawn_human_npc();
     SF_CHECK();
     command[ind] = n > 0 ? (char)actions[0] : '+';
+    if (g.online && !g.replay_mode) client.send_it();   // get_my_action(), gameplay.hpp:960-961
     for (int i = 1; i < 64 && i < n; ++i)
         g_hub.next_action[i] = action_index((char)actions[i]);
     g.zombie_action();
@@ -274,6 +320,11 @@ int sfref_step(const unsigned char *actions, int n)
     g.update_bull();
     ++g_steps;
     eval_end();
+    if (g.online && !g.replay_mode && (g_status == SF_DEAD || g_status == SF_WIN)) {
+        command[ind] = g_status == SF_DEAD ? '~' : '+';   // check_end(), gameplay.hpp:1103-1108, 1131-1136
+        client.send_it();
+        client.end_it();
+    }
     return g_status;
 #undef SF_CHECK
 #undef SF_UBGUARD

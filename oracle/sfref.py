@@ -115,6 +115,17 @@ def reset_replay(mode, level, path, squad_agents=False, caps=None, max_steps=0):
         raise RuntimeError("sfref_reset_ex failed")
 
 
+def reset_online(port, password, user="1", ip="127.0.0.1", caps=None, max_steps=0):
+    """Join a live online match with the reference's own client code (gameplay.hpp:66-193, 1807-1859);
+    returns this player's index.  Blocks until the server has everybody's sheet."""
+    L = lib()
+    with _InRundir():
+        rc = L.sfref_reset_online(ip.encode(), int(port), password.encode(), user.encode(), _caps_arr(caps), max_steps)
+    if rc < 0:
+        raise RuntimeError("sfref_reset_online failed (%d)" % rc)
+    return rc
+
+
 def step(actions):
     """actions: bytes, one command symbol per human slot (slot 0 = the player)."""
     L = lib()

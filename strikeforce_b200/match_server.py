@@ -1,4 +1,5 @@
-"""Match-server bridge -- STARTED, parity unpinned.
+"""Match-server bridge -- started; the wire protocol is pinned against the
+reference's own client code, the rules that depend on whose copy a match is are not yet.
 
 The reference's match server (StrikeForce-server/server.cpp) only relays: it accepts ``n`` players,
 tells everyone the seeds and the roster, and then, tick by tick, collects one command byte from every
@@ -19,8 +20,13 @@ Wire format, all messages NUL-terminated (server.cpp):
             (plus, once, the '_' of a player that just quit)
   :108-132  the match ends when the live players' teams no longer change along the index order
 
-Not pinned yet against the reference's own client code (planned: oracle/ref_harness, one process per
-player); the tests drive it with scripted socket clients and check the bytes and the arena.
+Pinning (tests/test_match_server.py): processes running the UNMODIFIED reference client (its
+network code through oracle/ref_harness: client.start / give_info / get_info / send_it / recieve)
+join a hosted match and every tick their copy of the match equals the host's arena, up to the header
+field that says which player the copy belongs to.  That test keeps to commands that never attack:
+the few rules that depend on `ind` (kill and loot credits, the own corpse keeping its cell, gameplay.hpp
+:591-592, 629-630, 642-645) differ between the copies by design, and the device arena is always the
+copy of seat 0.  Scripted socket clients check the bytes of quits, eliminations and the winner.
 """
 from __future__ import annotations
 

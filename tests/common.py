@@ -60,3 +60,6 @@ def golden_kwargs(g):
         if "sheets" in g:
             kw["sheets"] = [str(n) for n in g["sheets"]]
     return kw
+
+
+MATCH_TABLE = b"+qeawsd"  # commands that never attack (tests/test_match_server.py)

@@ -130,3 +130,82 @@ def test_protocol_roster_relay_quit_and_winner(arena_data):
         twin.step(r)
     assert arena.state_hash() == twin.state_hash() and len(rows) == 10
     host.close(), listener.close()
+
+
+CLIENT_SCRIPT = """
+import os, sys, zlib
+root, port, ticks = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
+    sys.path.insert(0, p)
+import common, sfref
+from strikeforce_b200 import config as sfcfg
+caps = [sfcfg.DEFAULT_CAPS[k] for k in common.CAP_KEYS]
+ind = sfref.reset_online(port, "pw", caps=caps)      # the reference's own client.start / give_info / get_info
+print("IND", ind, flush=True)
+for t in range(ticks):
+    c = common.MATCH_TABLE[common.splitmix_draw(77, ind, t) % len(common.MATCH_TABLE)]
+    st = sfref.step(bytes([c]))                       # client.send_it ... client.recieve inside human_action
+    rec = sfref.dump()
+    rec[10] = 0                                       # header field `ind`: every client is the ind of its own copy
+    print("H", t, st, zlib.crc32(rec.tobytes()), flush=True)
+"""
+
+
+def test_reference_clients_join_a_hosted_match(arena_data):
+    """PINS the protocol side: two processes run the UNMODIFIED reference client (its own network code,
+    gameplay.hpp:66-193, through oracle/ref_harness) against MatchHost; every tick the state of each
+    client's copy of the match equals the host's arena (the C oracle here) -- except the header field
+    that says which player the copy belongs to.  Commands that never attack keep the few other
+    ind-specific rules (kill credits, the own corpse) out of play."""
+    import subprocess
+    import sys
+    import zlib
+    import os
+    import pytest
+    import sfref
+    if not sfref.available():
+        pytest.skip("oracle/_ref/libsfref.so not built (needs /root/reference)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    teams, tb, serial, T = [1, 2], 1700000555, 99887, 400
+    listener = socket.socket()
+    listener.bind(("127.0.0.1", 0))
+    listener.listen(4)
+    port = listener.getsockname()[1]
+    host = ms.MatchHost(teams, "pw", tb, serial)
+    lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
+    lobby.start()
+    procs = [subprocess.Popen([sys.executable, "-c", CLIENT_SCRIPT, root, str(port), str(T)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for _ in teams]
+    try:
+        lobby.join(120)
+        assert sorted(host.socks) == [0, 1]
+        host.handshake()
+        account = "\n".join(l.strip() for l in open(sfref.ACCOUNT1).read().strip().splitlines())
+        assert all("\n".join(l.strip() for l in s.strip().splitlines()) == account for s in host.sheets.values())
+        cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False)
+        arena = sfo.Arena(cfg)
+        arena.reset(1, tb, serial)
+        mine = []
+
+        def step(row):
+            assert row == bytes(common.MATCH_TABLE[common.splitmix_draw(77, i, len(mine)) % len(common.MATCH_TABLE)]
+                                for i in range(2))
+            st = arena.step(row)
+            rec = arena.dump()
+            rec[10] = 0
+            mine.append((st, zlib.crc32(rec.tobytes())))
+
+        winner, ticks = ms.host_match(host, step, max_ticks=T)
+        assert ticks == T and winner == 0
+        for p in procs:
+            out, err = p.communicate(timeout=120)
+            lines = [l.split() for l in out.splitlines() if l.startswith("H ")]
+            assert len(lines) == T, out[-500:] + err[-2000:]
+            theirs = [(int(l[2]), int(l[3])) for l in lines]
+            bad = [t for t in range(T) if theirs[t] != mine[t]]
+            assert not bad, "client and host part at tick %d" % bad[0]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        host.close(), listener.close()

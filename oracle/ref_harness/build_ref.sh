@@ -29,9 +29,9 @@ echo '#include "bots/bot-0.5/Custom.hpp"'     > "$OUT/build/selected_custom.hpp"
 # run-time data
 rm -rf "$OUT/rundir/map" "$OUT/rundir/Items" "$OUT/rundir/character"
 cp -r "$REF/map" "$REF/Items" "$REF/character" "$OUT/rundir/"
-cp "$REF/accounts/game/1/info, 1.txt" "$OUT/rundir/player_account1.txt"
+cp -f "$REF/accounts/game/1/info, 1.txt" "$OUT/rundir/player_account1.txt"
 mkdir -p "$OUT/rundir/accounts/game/1"   # give_info() announces this file in a live online match
-cp "$REF/accounts/game/1/info, 1.txt" "$OUT/rundir/accounts/game/1/info, 1.txt"
+cp -f "$REF/accounts/game/1/info, 1.txt" "$OUT/rundir/accounts/game/1/info, 1.txt"
 g++ -std=c++17 -O2 -fPIC -shared -w \
     -I"$OUT/build" -I"$HERE/stubs" -I"$ROOT/include" \
     "$HERE/harness.cpp" -o "$OUT/libsfref.so" -lpthread

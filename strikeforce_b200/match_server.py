@@ -23,10 +23,12 @@ Wire format, all messages NUL-terminated (server.cpp):
 Pinning (tests/test_match_server.py): processes running the UNMODIFIED reference client (its
 network code through oracle/ref_harness: client.start / give_info / get_info / send_it / recieve)
 join a hosted match and every tick their copy of the match equals the host's arena, up to the header
-field that says which player the copy belongs to.  That test keeps to commands that never attack:
-the few rules that depend on `ind` (kill and loot credits, the own corpse keeping its cell, gameplay.hpp
-:591-592, 629-630, 642-645) differ between the copies by design, and the device arena is always the
-copy of seat 0.  Scripted socket clients check the bytes of quits, eliminations and the winner.
+field that says which player the copy belongs to (400 ticks of commands that never attack).  With
+the whole alphabet (1,500 ticks) the client in seat 0 -- the seat whose copy the host's arena is --
+still matches completely, the other one in everything but the header counters and the cells: the few
+rules that depend on `ind` (kill and loot credits, the own corpse keeping its cell, gameplay.hpp
+:591-592, 629-630, 642-645) differ between the copies by design.  Scripted socket clients check the
+bytes of quits, eliminations and the winner.
 """
 from __future__ import annotations
 

@@ -63,3 +63,19 @@ def golden_kwargs(g):
 
 
 MATCH_TABLE = b"+qeawsd"  # commands that never attack (tests/test_match_server.py)
+
+
+def record_crcs(rec):
+    """(crc of the whole canonical record with the header field `ind` cleared, crc of the record
+    without header and cells): the second one is what every client's copy of an online match shares
+    with every other copy even after kills (credits go to `ind` only, a dead `ind` keeps its cell)."""
+    import zlib
+    rec = np.array(rec, dtype=np.int32)
+    rec[10] = 0
+    kept, i = [], 0
+    while i + 3 <= len(rec):
+        n = 3 + int(rec[i + 2])
+        if int(rec[i]) not in (1, 7):
+            kept.append(rec[i:i + n])
+        i += n
+    return zlib.crc32(rec.tobytes()), zlib.crc32(np.concatenate(kept).tobytes())

@@ -134,7 +134,7 @@ def test_protocol_roster_relay_quit_and_winner(arena_data):
 
 CLIENT_SCRIPT = """
 import os, sys, zlib
-root, port, ticks = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+root, port, ticks, table = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4].encode()
 for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
     sys.path.insert(0, p)
 import common, sfref
@@ -143,30 +143,25 @@ caps = [sfcfg.DEFAULT_CAPS[k] for k in common.CAP_KEYS]
 ind = sfref.reset_online(port, "pw", caps=caps)      # the reference's own client.start / give_info / get_info
 print("IND", ind, flush=True)
 for t in range(ticks):
-    c = common.MATCH_TABLE[common.splitmix_draw(77, ind, t) % len(common.MATCH_TABLE)]
+    c = table[common.splitmix_draw(77, ind, t) % len(table)]
     st = sfref.step(bytes([c]))                       # client.send_it ... client.recieve inside human_action
-    rec = sfref.dump()
-    rec[10] = 0                                       # header field `ind`: every client is the ind of its own copy
-    print("H", t, st, zlib.crc32(rec.tobytes()), flush=True)
+    full, shared = common.record_crcs(sfref.dump())   # `ind` cleared: every client is the ind of its own copy
+    print("H", t, st, full, shared, flush=True)
+    if st != 0:
+        break
 """
 
 
-def test_reference_clients_join_a_hosted_match(arena_data):
-    """PINS the protocol side: two processes run the UNMODIFIED reference client (its own network code,
-    gameplay.hpp:66-193, through oracle/ref_harness) against MatchHost; every tick the state of each
-    client's copy of the match equals the host's arena (the C oracle here) -- except the header field
-    that says which player the copy belongs to.  Commands that never attack keep the few other
-    ind-specific rules (kill credits, the own corpse) out of play."""
+def _hosted_match_with_reference_clients(arena_data, table, T):
+    import os
     import subprocess
     import sys
-    import zlib
-    import os
     import pytest
     import sfref
     if not sfref.available():
         pytest.skip("oracle/_ref/libsfref.so not built (needs /root/reference)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    teams, tb, serial, T = [1, 2], 1700000555, 99887, 400
+    teams, tb, serial = [1, 2], 1700000555, 99887
     listener = socket.socket()
     listener.bind(("127.0.0.1", 0))
     listener.listen(4)
@@ -174,8 +169,8 @@ def test_reference_clients_join_a_hosted_match(arena_data):
     host = ms.MatchHost(teams, "pw", tb, serial)
     lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
     lobby.start()
-    procs = [subprocess.Popen([sys.executable, "-c", CLIENT_SCRIPT, root, str(port), str(T)], stdout=subprocess.PIPE,
-                              stderr=subprocess.PIPE, text=True) for _ in teams]
+    procs = [subprocess.Popen([sys.executable, "-c", CLIENT_SCRIPT, root, str(port), str(T), table.decode()],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in teams]
     try:
         lobby.join(120)
         assert sorted(host.socks) == [0, 1]
@@ -188,24 +183,50 @@ def test_reference_clients_join_a_hosted_match(arena_data):
         mine = []
 
         def step(row):
-            assert row == bytes(common.MATCH_TABLE[common.splitmix_draw(77, i, len(mine)) % len(common.MATCH_TABLE)]
-                                for i in range(2))
-            st = arena.step(row)
-            rec = arena.dump()
-            rec[10] = 0
-            mine.append((st, zlib.crc32(rec.tobytes())))
+            if arena.status() == 0:
+                st = arena.step(row)
+                mine.append((st,) + common.record_crcs(arena.dump()))
 
         winner, ticks = ms.host_match(host, step, max_ticks=T)
-        assert ticks == T and winner == 0
+        results = {}
         for p in procs:
             out, err = p.communicate(timeout=120)
+            ind = int([l for l in out.splitlines() if l.startswith("IND")][0].split()[1])
             lines = [l.split() for l in out.splitlines() if l.startswith("H ")]
-            assert len(lines) == T, out[-500:] + err[-2000:]
-            theirs = [(int(l[2]), int(l[3])) for l in lines]
-            bad = [t for t in range(T) if theirs[t] != mine[t]]
-            assert not bad, "client and host part at tick %d" % bad[0]
+            assert lines, out[-500:] + err[-2000:]
+            results[ind] = [(int(l[2]), int(l[3]), int(l[4])) for l in lines]
+        return mine, results, winner, ticks
     finally:
         for p in procs:
             if p.poll() is None:
                 p.kill()
         host.close(), listener.close()
+
+
+def test_reference_clients_join_a_hosted_match(arena_data):
+    """PINS the protocol side: two processes run the UNMODIFIED reference client (its own network code,
+    gameplay.hpp:66-193, through oracle/ref_harness) against MatchHost; every tick the state of each
+    client's copy of the match equals the host's arena (the C oracle here) -- except the header field
+    that says which player the copy belongs to.  Commands that never attack keep the few other
+    ind-specific rules (kill credits, the own corpse) out of play."""
+    T = 400
+    mine, results, winner, ticks = _hosted_match_with_reference_clients(arena_data, common.MATCH_TABLE, T)
+    assert ticks == T and winner == 0 and len(mine) == T
+    for ind, theirs in results.items():
+        assert len(theirs) == T
+        bad = [t for t in range(T) if theirs[t][:2] != mine[t][:2]]
+        assert not bad, "client %d and the host part at tick %d" % (ind, bad[0])
+
+
+def test_reference_clients_fight_in_a_hosted_match(arena_data):
+    """The same with the whole alphabet (shots, throwables, blocks, portals): the client that holds
+    seat 0 -- the seat whose copy the host's arena is -- must match it completely; the other client's
+    copy may differ in what depends on `ind` (header counters, cells) and must match in everything
+    else: RNG state, every human, zombie, bullet and portal."""
+    T = 1500
+    mine, results, winner, ticks = _hosted_match_with_reference_clients(arena_data, sfcfg.ACTIONS28, T)
+    n = min(len(mine), min(len(r) for r in results.values()))
+    assert n >= 200
+    for t in range(n):
+        assert results[0][t][:2] == mine[t][:2], "seat 0's client and the host part at tick %d" % t
+        assert results[1][t][2] == mine[t][2], "seat 1's client and the host part at tick %d" % t

@@ -150,7 +150,8 @@ int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb,
    (gameplay.hpp:43) as filled by get_my_action / get_command (gameplay.hpp:929-963). */
 int sf_step(sf_handle *h, const uint8_t *actions, void *stream);
 
-/* The two halves of sf_step, for callers that need the P2 observation point
+/* The two halves of sf_step (always called in pairs: a second sf_step_a, or sf_step, before the
+   sf_step_b that closes the first is SF_ERR_ARG), for callers that need the P2 observation point
    (get_command -> bot() inside human_action, gameplay.hpp:933): sf_step_a runs the spawns and
    half-tick A (gameplay.hpp:1444-1461), sf_observe(..., SF_OBS_P2, ...) then sees what the
    squad agents see, and sf_step_b applies the actions and runs half-tick B (:1462-1471). */
@@ -171,7 +172,9 @@ int sf_synth_actions(sf_handle *h, uint8_t *actions, uint64_t t, const char *tab
 
 /* Replaces gameplay::bot() up to the Agent::predict call (bots/bot-0.5/Custom.hpp:137-158):
    writes the fp32 [n_envs][n_obs_agents][32][31][31] observation of the driven humans into the
-   DEVICE buffer obs.  agent_mask bit a selects human slot a (bit 0 = the player). */
+   DEVICE buffer obs.  agent_mask bit a selects human slot a (bit 0 = the player).  phase names the
+   observation point the caller is at and must match the handle: SF_OBS_P2 between sf_step_a and
+   sf_step_b, SF_OBS_P1 otherwise (SF_ERR_ARG if it does not). */
 int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, void *stream);
 
 /* Copy a per-arena field into a DEVICE buffer (sizes above). */

@@ -6,10 +6,11 @@
  * overflow, out-of-bounds guard, end-of-step victory test) this file shares so that the two
  * can be compared record for record.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py compares the canonical record
+ * Parity status: PINNED.  tests/test_oracle_golden.py compares the canonical record
  * (include/sf_canon.h) of this model with oracle/_ref/libsfref.so after every step over
- * seeded matches in all three modes, and tests/golden/ holds records produced by the
- * reference itself (tests/golden/make_golden.py).
+ * seeded matches (test_oracle_matches_reference_live; tests/test_royale_reference_live.py for
+ * Battle Royale), and tests/golden/ holds records produced by the reference itself
+ * (tests/golden/make_golden.py, make_golden_royale.py).
  */
 #include "sf_oracle.h"
 

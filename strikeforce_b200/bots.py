@@ -86,6 +86,26 @@ class Custom:
     def view(self, sim):
         return None
 
+    def agents(self):
+        """every agent object this Custom drives (one by default)"""
+        return [self.agent]
+
+    def new_games(self, sim, done):
+        """``done``: bool device tensor [n_envs], arenas whose episode ended in the last step.  The
+        reference plays one game per process and builds a new ``Agent`` for the next one
+        (``prepare``, Custom.hpp:161-165); with auto-reset the batch equivalent is to reset the rows
+        of those arenas (every driven human of an arena is a run of consecutive rows)."""
+        for a in self.agents():
+            reset = getattr(a, "reset_rows", None)
+            rows = getattr(a, "calls", None)
+            if reset is not None and rows is not None:
+                reset(done.repeat_interleave(rows.shape[0] // sim.n_envs))
+
+
+def _finish_step(sim, custom):
+    custom.view(sim)
+    custom.new_games(sim, sim.step_out()[:, 0] != sfcfg.RUNNING)
+
 
 def play(sim, custom: Custom, steps: int):
     """The loop of gameplay::play() (gameplay.hpp:1443-1472) for a batch of arenas; returns the
@@ -99,7 +119,7 @@ def play(sim, custom: Custom, steps: int):
         for _ in range(steps):
             actions[:] = custom.bot(sim, (1 << sim.n_agents) - 1, sfcfg.OBS_P1)
             sim.step(actions)
-            custom.view(sim)
+            _finish_step(sim, custom)
         return sim.stats()
     for _ in range(steps):
         actions[:, 0:1] = custom.bot(sim, 1, sfcfg.OBS_P1)  # get_my_action, :956
@@ -110,5 +130,5 @@ def play(sim, custom: Custom, steps: int):
             sim.step_b(actions)
         else:
             sim.step(actions)
-        custom.view(sim)
+        _finish_step(sim, custom)
     return sim.stats()

@@ -13,6 +13,7 @@
 
 /* sinks: a flat int32 buffer, or the order-independent hash */
 struct SfBufSink {
+    static constexpr bool ordered = true; /* elements in record order (cells by index) */
     int32_t *buf;
     long cap, n;
     bool overflow;
@@ -27,6 +28,7 @@ struct SfBufSink {
     }
 };
 struct SfHashSink {
+    static constexpr bool ordered = false; /* a sum: any order */
     uint64_t sum;
     SF_MFN void elem(int kind, int index, const int32_t *f, int nf)
     {
@@ -35,6 +37,23 @@ struct SfHashSink {
         sum += h;
     }
 };
+
+/* one SF_K_CELL element */
+template <class Sink>
+SF_FN void sf_canon_cell(const SfDev &d, int env, const SfEnv &e, int cell, int lin, uint32_t g, int bidx, Sink &sink)
+{
+    int32_t f[SF_NF_CELL];
+    uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+    bool chest = kind >= K_CHEST0 && kind < K_BLOCK;
+    int built = kind == K_BLOCK ? 1 : kind == K_ENTRANCE ? 2 : kind == K_EXIT ? 3 : 0;
+    int q = built ? sf_find_built(d, env, e, cell) : -1;
+    f[0] = (g & C_S0) ? 1 : 0, f[1] = (g & C_S0) ? (int32_t)(g & C_OCC) : -1;
+    f[2] = (g & C_S1) ? 1 : 0, f[3] = (g & C_S1) ? (int32_t)(g & C_OCC) : -1;
+    f[4] = bidx >= 0 ? 1 : 0, f[5] = bidx;
+    f[6] = chest ? 1 : 0, f[7] = chest ? (int32_t)kind - K_CHEST0 : -1;
+    f[8] = built, f[9] = q >= 0 ? SF_T(d.t_dmg, q) : 0, f[10] = built == 2 ? (int32_t)SF_T(d.t_pidx, q) : -1;
+    sink.elem(SF_K_CELL, lin, f, SF_NF_CELL);
+}
 
 template <class Sink>
 SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int env, Sink &sink)
@@ -45,7 +64,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
     f[0] = k.mode, f[1] = e.level, f[2] = (int32_t)e.frame, f[3] = e.kills, f[4] = e.tkills, f[5] = e.loot;
     f[6] = e.chest, f[7] = 0;
     sink.elem(SF_K_HEADER, 0, f, SF_NF_HEADER);
-    for (int i = 0; i < 18; ++i) f[i] = (int32_t)t.exp_tab[sf_rng_log(e, i)] + 1;
+    for (int i = 0; i < 18; ++i) f[i] = (int32_t)sf_exp_m1(t, 2u * sf_rng_log(e, i)) + 1;
     f[18] = (int32_t)(e.jomle & 0xFFFFu);
     sink.elem(SF_K_RNG, 0, f, SF_NF_RNG);
     for (int h = 0; h < e.hw_h; ++h) {
@@ -88,26 +107,31 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
         sf_tcell_decode(sf_exit_cell(d, k, env, p), &f[0], &f[1], &f[2]);
         sink.elem(SF_K_PORTAL, p, f, SF_NF_PORTAL);
     }
+    /* the bullet flags of the record (s2, bidx) come from the owning bullets; their cells first */
+    uint16_t oc[SF_LIM_BULLETS];
+    int16_t ob[SF_LIM_BULLETS];
+    int n_own = 0;
+    for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1))
+        if (SF_AT(d.b_meta, b) & BF_OWNS) oc[n_own] = (uint16_t)(SF_AT(d.b_pw, b) & POS_CELL), ob[n_own++] = (int16_t)b;
     for (int lin = 0; lin < SF_CELLS; ++lin) { /* the record lists cells in the reference's (floor, row, col) order */
         const int cell = sf_tcell(lin / (SF_ROWS * SF_COLS), (lin / SF_COLS) % SF_ROWS, lin % SF_COLS);
         uint32_t g = SF_G(cell);
-        if (!g) continue;
-        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-        if (!(g & (C_S0 | C_S1 | C_S2)) && kind == K_NONE) continue;
         int bidx = -1;
-        if (g & C_S2)
-            for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1))
-                if ((SF_AT(d.b_meta, b) & BF_OWNS) && (int)(SF_AT(d.b_pw, b) & POS_CELL) == cell) bidx = b;
-        bool chest = kind >= K_CHEST0 && kind < K_BLOCK;
-        int built = kind == K_BLOCK ? 1 : kind == K_ENTRANCE ? 2 : kind == K_EXIT ? 3 : 0;
-        int q = built ? sf_find_built(d, env, e, cell) : -1;
-        f[0] = (g & C_S0) ? 1 : 0, f[1] = (g & C_S0) ? (int32_t)(g & C_OCC) : -1;
-        f[2] = (g & C_S1) ? 1 : 0, f[3] = (g & C_S1) ? (int32_t)(g & C_OCC) : -1;
-        f[4] = (g & C_S2) ? 1 : 0, f[5] = bidx;
-        f[6] = chest ? 1 : 0, f[7] = chest ? (int32_t)kind - K_CHEST0 : -1;
-        f[8] = built, f[9] = q >= 0 ? SF_T(d.t_dmg, q) : 0, f[10] = built == 2 ? (int32_t)SF_T(d.t_pidx, q) : -1;
-        sink.elem(SF_K_CELL, lin, f, SF_NF_CELL);
+        if (Sink::ordered || g)
+            for (int i = 0; i < n_own; ++i)
+                if (oc[i] == cell) bidx = ob[i];
+        uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
+        if (!Sink::ordered && !g) continue; /* cells that carry a bullet flag only follow below */
+        if (!(g & (C_S0 | C_S1)) && bidx < 0 && kind == K_NONE) continue;
+        sf_canon_cell(d, env, e, cell, lin, g, bidx, sink);
     }
+    if (!Sink::ordered)
+        for (int i = 0; i < n_own; ++i)
+            if (!SF_G(oc[i])) {
+                int f0, r0, c0;
+                sf_tcell_decode(oc[i], &f0, &r0, &c0);
+                sf_canon_cell(d, env, e, oc[i], (f0 * SF_ROWS + r0) * SF_COLS + c0, 0u, ob[i], sink);
+            }
 }
 
 #endif

@@ -56,15 +56,20 @@
 #define SF_PHASE_SYNC(n) ((void)0)
 #endif
 
+#ifdef SF_DEBUG_HIST
+static unsigned long long sf_dbg_hist[256]; /* host-check builds only: flagged cells per arena when the bullets are resolved */
+#endif
 #define SF_RNG_ZERO 0x10000u /* log-domain marker of the value 0 (only during the warm-up) */
 
 /* tables every lane reads: shared memory on the device, plain arrays in the host check */
 struct SfTabs {
     const uint8_t *smap;     /* static map bytes [SF_TCELLS], tiled cell ids */
-    const uint16_t *exp_tab; /* [65536] */
+    const uint16_t *exp_tab; /* [32768]: the first half of 3^k - 1; the rest follows from 3^32768 = -1 (sf_exp_m1) */
     const uint16_t *log_tab; /* [65536] */
     const uint32_t *rng_cst; /* [2][18][E] per-arena term constants (terms 10..17 are read on demand) */
     int32_t E;
+    uint16_t *bt;            /* this arena's table of flagged cells: entry i at bt[i * bt_stride] (sf_bt_*) */
+    int32_t bt_stride;
 };
 
 /* register-resident part of one arena while a kernel works on it */
@@ -81,7 +86,7 @@ struct SfEnv {
     uint32_t W;          /* sum of the values random[10..17] (see sf_rand) */
     bool fast;           /* both seeds below 10^10: terms 10..17 are the plain window W */
     bool bank;           /* which half of rng_cst holds this stream's term constants */
-    bool watch;          /* something may stand on a portal exit (sf_portal_damage); false = provably nothing */
+    bool watch;          /* a human may stand on a portal exit (sf_portal_damage); false = provably none */
 };
 
 /* ------------------------------------------------------------------ small helpers */
@@ -186,9 +191,10 @@ SF_FN bool sf_neighbour(int cell, int d, int *out)
     return !(r >= SF_ROWS || r < 0 || c >= SF_COLS || c < 0);
 }
 
-/* node::showit(), gameplay.hpp:321-341, from the static byte and the overlay word.  s[8]
- * (death mark) is render-only: updmap() clears it before any rule reads a cell (:489-495). */
-SF_FN int sf_showit(uint32_t st, uint32_t g)
+/* node::showit(), gameplay.hpp:321-341, from the static byte, the overlay word and the cell's
+ * bullet flag s[2] (which is not stored in the overlay: sf_owner_at).  s[8] (death mark) is
+ * render-only: updmap() clears it before any rule reads a cell (:489-495). */
+SF_FN int sf_showit(uint32_t st, uint32_t g, bool s2)
 {
     uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
     if ((st & M_WALL) || kind == K_BLOCK) return SH_WALL;
@@ -196,7 +202,7 @@ SF_FN int sf_showit(uint32_t st, uint32_t g)
     if (g & C_S1) return SH_ZOMBIE;
     if ((st & M_UP) || kind == K_ENTRANCE) return SH_UP;
     if (st & M_DOWN) return SH_DOWN;
-    if (g & C_S2) return SH_BULLET;
+    if (s2) return SH_BULLET;
     if (kind >= K_CHEST0 && kind < K_BLOCK) return SH_CHEST;
     if ((st & M_EXIT) || kind == K_EXIT) return SH_EXIT;
     return SH_DOT;
@@ -221,10 +227,19 @@ SF_FN bool sf_is_exit(const SfTabs &t, int cell, uint32_t g)
  * leading terms; a lane with longer seeds takes the eight extra look-ups itself. */
 SF_FN uint32_t sf_rng_log(const SfEnv &e, int i) { return (e.Lp[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; }
 
+/* 3^k mod 65537, minus one, for k2 = 2 * k (k < 65536).  Only the first half of the table is kept
+ * (64 KB of shared memory instead of 128 KB -- the other half holds the bullet-flag tables of the
+ * CTA's arenas): 3^32768 = -1 (mod 65537), so 3^(k + 32768) - 1 = 65536 - 3^k = 65535 - (3^k - 1),
+ * the 16-bit complement of the entry. */
+SF_FN uint32_t sf_exp_m1(const SfTabs &t, uint32_t k2)
+{
+    const uint32_t v = *(const uint16_t *)((const uint8_t *)t.exp_tab + (k2 & 0xFFFEu));
+    return (k2 & 0x10000u) ? (v ^ 0xFFFFu) : v;
+}
+
 SF_FN uint32_t sf_rng_term(const SfTabs &t, uint32_t L, uint32_t c)
 {
-    uint32_t off = (L * (c & 0xFFu) + (c >> 8)) & 0x1FFFEu;
-    return *(const uint16_t *)((const uint8_t *)t.exp_tab + off);
+    return sf_exp_m1(t, (L * (c & 0xFFu) + (c >> 8)) & 0x1FFFEu);
 }
 
 SF_FN int sf_rand(SfEnv &e, const SfTabs &t)
@@ -246,8 +261,8 @@ SF_FN int sf_rand(SfEnv &e, const SfTabs &t)
     uint32_t lg = t.log_tab[r - 1];
     e.jomle += 1;
     uint32_t ln = (lg * (e.jomle & 0xFFFFu)) & 0xFFFFu;       /* binpow(sum, jomle), :42-52 */
-    uint32_t val = (uint32_t)t.exp_tab[ln] + 1u;
-    e.W += val - ((uint32_t)t.exp_tab[sf_rng_log(e, 10)] + 1u); /* element 10 leaves the window */
+    uint32_t val = sf_exp_m1(t, 2u * ln) + 1u;
+    e.W += val - (sf_exp_m1(t, 2u * sf_rng_log(e, 10)) + 1u); /* element 10 leaves the window */
     SF_UNROLL
     for (int j = 0; j < 8; ++j) e.Lp[j] = (e.Lp[j] >> 16) | (e.Lp[j + 1] << 16);
     e.Lp[8] = (e.Lp[8] >> 16) | (ln << 16);
@@ -348,7 +363,7 @@ SF_FN void sf_install_stream(const SfDev &d, const SfTabs &t, int env, SfEnv &e,
     for (int i = 0; i < 10; ++i) e.cst[i] = d.rng_cst[sf_cst_index(d, e.bank ? 1 : 0, i, env)];
     e.jomle = 18u + SF_WARM_DRAWS;
     e.W = 0;
-    for (int i = 10; i < 18; ++i) e.W += (uint32_t)t.exp_tab[sf_rng_log(e, i)] + 1u;
+    for (int i = 10; i < 18; ++i) e.W += sf_exp_m1(t, 2u * sf_rng_log(e, i)) + 1u;
     /* the header must carry the new bank before the next pending stream is addressed */
     d.misc[env] = (d.misc[env] & ~(1u << 25)) | (e.bank ? 1u << 25 : 0u);
     sf_seed_pending(d, t, env, e.bank ? 0 : 1, next_tb, next_serial);
@@ -400,26 +415,163 @@ SF_FN int sf_alloc_bullet(const SfConst &k, SfEnv &e)
     return b;
 }
 
-/* a new bullet becomes the cell's last writer (node::bullet under s[2]); any older owner of
- * the same cell keeps flying but loses the flag */
-SF_FN void sf_place_bullet(const SfDev &d, int env, SfEnv &e, int b, int cell, uint32_t g, int way0, int range,
-                           int owner, int dmg, int eff)
+/* ---- the bullet flag s[2] ------------------------------------------------------------------
+ * node::s[2] ("a bullet is here") and node::bullet (its last writer, gameplay.hpp:237-243) are not
+ * stored per cell: s[2] of a cell is set exactly while one live bullet standing in it carries
+ * BF_OWNS -- that bullet is the last writer -- so both are a property of the bullet list.  Moving
+ * bullets are the bulk of all cell updates of a step (set at the new cell, cleared at the old one,
+ * every half-tick), and on this layout a cell update is a scattered 2-byte write into a 2.6 GB
+ * overlay; deriving the flag instead removes those writes and the look-ahead read of update_bull.
+ *
+ * "Is there a bullet flag on this cell?" is answered by a per-arena TABLE in shared memory: an
+ * open-addressing hash set (linear probing) of the flagged cells, SF_BT_SLOTS 16-bit entries
+ * (cell + 1, 0 = empty) plus a count.  One lane's rare event is its whole warp's wait -- and, with
+ * the phase barriers, its whole CTA's -- so nothing on this path may be slow, not even the
+ * overflow: an arena with more than SF_BT_FULL flagged cells (1% of the arenas of the benchmark
+ * at any time) SPILLS the next flags into the overlay word of their cell (C_S2, the bit the
+ * reference keeps there), marks their bullets BF_SPILL and raises SF_BT_SPILL in its count; while
+ * that is up a look-up that misses the table also reads the cell.  sf_resolve_bullets, which
+ * consumes every flag, clears the spilled bits through their bullets and wipes the table.  The
+ * table is rebuilt from the bullet rows when a kernel picks an arena up. */
+#ifndef SF_BT_SLOTS
+#define SF_BT_SLOTS 47
+#define SF_BT_FULL 40
+#endif
+#define SF_BT_ENTRIES (SF_BT_SLOTS + 1) /* 48 x uint16 = 24 words per arena */
+#define SF_BT_SPILL 0x8000u
+SF_FN uint16_t &sf_bt_at(const SfTabs &t, int i) { return t.bt[i * t.bt_stride]; }
+SF_FN void sf_bt_wipe(const SfTabs &t)
 {
-    if (g & C_S2) { /* rare, and always inside divergent code: a plain early-exit walk over the live bullets */
-        for (int o = m2_next(e.mb, 0); o >= 0; o = m2_next(e.mb, o + 1)) {
-            if (o == b) continue;
-            uint32_t m = SF_AT(d.b_meta, o);
-            if ((m & BF_OWNS) && (int)(SF_AT(d.b_pw, o) & POS_CELL) == cell) {
-                SF_AT(d.b_meta, o) = m & ~BF_OWNS;
-                break;
+    SF_UNROLL
+    for (int i = 0; i < SF_BT_ENTRIES; ++i) sf_bt_at(t, i) = 0;
+}
+/* the slot that holds `cell`, or -1 - (the empty slot where it would go) */
+SF_FN int sf_bt_find(const SfTabs &t, int cell)
+{
+    const uint32_t key = (uint32_t)cell + 1u;
+    int i = (int)(((((uint32_t)cell * 40503u) >> 3) & 0xFFFFu) * SF_BT_SLOTS >> 16);
+    SF_NO_UNROLL
+    for (;;) {
+        const uint32_t v = sf_bt_at(t, i);
+        if (v == key) return i;
+        if (v == 0u) return -1 - i;
+        i = i + 1 == SF_BT_SLOTS ? 0 : i + 1;
+    }
+}
+/* node::s[2] of `cell` */
+SF_FN bool sf_flagged(const SfDev &d, const SfTabs &t, int env, int cell)
+{
+    if (sf_bt_find(t, cell) >= 0) return true;
+    return (sf_bt_at(t, SF_BT_SLOTS) & SF_BT_SPILL) && (SF_G(cell) & C_S2);
+}
+/* raise the flag of `cell`: 0 = it was up already (in the table), SF_FLAG_NEW = raised in the
+ * table, and with BF_SPILL or'ed in: ... in the overlay (the bullet that owns the flag carries
+ * that bit: it is the one that takes the flag down again) */
+#define SF_FLAG_NEW 1u
+SF_FN uint32_t sf_flag_cell(const SfDev &d, const SfTabs &t, int env, int cell)
+{
+    const int i = sf_bt_find(t, cell);
+    if (i >= 0) return 0u;
+    const uint32_t n = sf_bt_at(t, SF_BT_SLOTS);
+    if (n & SF_BT_SPILL) { /* some flags of this arena live in the overlay: this one? */
+        const uint32_t g = SF_G(cell);
+        if (g & C_S2) return BF_SPILL;
+        if ((n & ~SF_BT_SPILL) >= SF_BT_FULL) {
+            SF_G(cell) = (uint16_t)(g | C_S2);
+            return SF_FLAG_NEW | BF_SPILL;
+        }
+    } else if (n >= SF_BT_FULL) {
+        SF_G(cell) = (uint16_t)(SF_G(cell) | C_S2);
+        sf_bt_at(t, SF_BT_SLOTS) = (uint16_t)(n | SF_BT_SPILL);
+        return SF_FLAG_NEW | BF_SPILL;
+    }
+    sf_bt_at(t, -1 - i) = (uint16_t)(cell + 1);
+    sf_bt_at(t, SF_BT_SLOTS) = (uint16_t)(n + 1u);
+    return SF_FLAG_NEW;
+}
+
+/* the live bullet that owns `cell` (slot `skip` left out), -1 if none: a walk over the bullet
+ * rows, eight positions in flight at a time.  Needed only when a bullet is put on a cell that is
+ * flagged already (the old last writer loses BF_OWNS) and by the kernels outside the tick; one
+ * out-of-line copy that takes plain values, so the arena's registers stay where they are. */
+SF_COLD int sf_owner_walk(const uint16_t *pw, const uint32_t *meta, size_t stride, uint64_t m0, uint64_t m1, int cell,
+                          int skip)
+{
+    SF_NO_UNROLL
+    for (int half = 0; half < 2; ++half) {
+        uint64_t m = half ? m1 : m0;
+        SF_NO_UNROLL
+        while (m) {
+            int o[8];
+            uint32_t p[8];
+            SF_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                o[j] = m ? half * 64 + sf_ffs64(m) : -1;
+                m &= m - 1; /* 0 stays 0 */
+                p[j] = o[j] >= 0 ? (uint32_t)pw[(size_t)o[j] * stride] : 0xFFFFu;
             }
+            SF_UNROLL
+            for (int j = 0; j < 8; ++j)
+                if ((int)(p[j] & POS_CELL) == cell && o[j] >= 0 && o[j] != skip && (meta[(size_t)o[j] * stride] & BF_OWNS))
+                    return o[j];
         }
     }
+    return -1;
+}
+SF_FN int sf_owner_scan(const SfDev &d, int env, const SfEnv &e, int cell, int skip)
+{
+    return sf_owner_walk(d.b_pw + env, d.b_meta + env, (size_t)d.E, e.mb[0], e.mb[1], cell, skip);
+}
+
+/* rebuild the table from the bullet rows (the owning bullets of a resting arena are exact; the
+ * spilled flags are in the overlay already) */
+SF_FN void sf_bt_rebuild(const SfDev &d, const SfTabs &t, int env, const SfEnv &e)
+{
+    sf_bt_wipe(t);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
+    const uint64_t live0 = e.on ? e.mb[0] : 0ull, live1 = e.on ? e.mb[1] : 0ull;
+    for (int b0 = 0; b0 <= hi; b0 += 4) {
+        uint32_t pw[4], meta[4];
+        SF_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + j;
+            const bool lv = b <= hi && (((b < 64 ? live0 : live1) >> (b & 63)) & 1);
+            pw[j] = lv ? (uint32_t)SF_AT(d.b_pw, b) : 0u;
+            meta[j] = lv ? SF_AT(d.b_meta, b) : 0u;
+        }
+        SF_NO_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t mj = j == 0 ? meta[0] : j == 1 ? meta[1] : j == 2 ? meta[2] : meta[3];
+            const uint32_t pj = j == 0 ? pw[0] : j == 1 ? pw[1] : j == 2 ? pw[2] : pw[3];
+            if (mj & BF_SPILL) sf_bt_at(t, SF_BT_SLOTS) = (uint16_t)(sf_bt_at(t, SF_BT_SLOTS) | SF_BT_SPILL);
+            else if (mj & BF_OWNS) {
+                const uint32_t fl = sf_flag_cell(d, t, env, (int)(pj & POS_CELL));
+                if (fl & BF_SPILL) SF_AT(d.b_meta, b0 + j) = mj | BF_SPILL; /* never: the table held them before */
+            }
+        }
+        SF_SYNCWARP();
+    }
+}
+
+/* a new bullet becomes the cell's last writer (node::bullet under s[2]); any older owner of
+ * the same cell keeps flying but loses the flag */
+SF_FN void sf_write_bullet(const SfDev &d, int env, int b, int cell, int way0, int range, int owner, int dmg, int eff,
+                           uint32_t fl)
+{
     SF_AT(d.b_pw, b) = (uint16_t)(cell | (way0 << POS_HI_SHIFT));
-    SF_AT(d.b_meta, b) = (uint32_t)range | ((uint32_t)(owner + 1) << 16) | BF_OWNS;
+    SF_AT(d.b_meta, b) = (uint32_t)range | ((uint32_t)(owner + 1) << 16) | BF_OWNS | (fl & BF_SPILL);
     SF_AT(d.b_dmg, b) = dmg;
     SF_AT(d.b_eff, b) = eff;
-    SF_G(cell) = (uint16_t)(g | C_S2);
+}
+SF_FN void sf_place_bullet(const SfDev &d, const SfTabs &t, int env, SfEnv &e, int b, int cell, int way0, int range,
+                           int owner, int dmg, int eff)
+{
+    const uint32_t fl = sf_flag_cell(d, t, env, cell);
+    if (!(fl & SF_FLAG_NEW)) { /* rare, and always inside divergent code */
+        int o = sf_owner_scan(d, env, e, cell, b);
+        if (o >= 0) SF_AT(d.b_meta, o) = SF_AT(d.b_meta, o) & ~(BF_OWNS | BF_SPILL);
+    }
+    sf_write_bullet(d, env, b, cell, way0, range, owner, dmg, eff, fl);
 }
 
 /* slot of the player-built record of `cell` in the temp list (gameplay.hpp:469), -1 if none.
@@ -520,7 +672,7 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
         }
         int cell = sf_cell_of(i, j, c);
         bool dot = false;
-        if (due) dot = sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT;
+        if (due) dot = sf_showit(t.smap[cell], SF_G(cell), false) == SH_DOT && !sf_flagged(d, t, env, cell);
         int z = 0;
         if (dot && kind == 1) {
             z = m2_lowest_free(e.mz);
@@ -561,10 +713,12 @@ SF_FN void sf_spawns(const SfDev &d, const SfConst &k, const SfTabs &t, int env,
 
 /* ------------------------------------------------------------------ half-tick pieces */
 
-/* zombie_action, gameplay.hpp:654-693.  Two zombies per round: their positions, then their own
- * cell and four neighbours, are loaded back to back (ten independent loads in flight) before
- * the rules run in slot order; what the first zombie writes is forwarded into the second
- * zombie's loaded copy so that it sees exactly what a sequential walk would. */
+/* zombie_action, gameplay.hpp:654-693.  Two zombies per round: their positions, then their four
+ * neighbours, are loaded back to back (eight independent loads in flight) before the rules run in
+ * slot order; what the first zombie writes is forwarded into the second zombie's loaded copy so
+ * that it sees exactly what a sequential walk would.  A zombie's own cell is never read: it holds
+ * the zombie and nothing else (zombies only enter cells that print '.', and nothing is built or
+ * dropped on an occupied cell), and its bullet flag comes from the table. */
 SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mz) : -1);
@@ -581,7 +735,7 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
         bool act[2];
         uint32_t pw[2];
         int cell[2];
-        uint32_t gv[2][5];
+        uint32_t gv[2][4];
         SF_UNROLL
         for (int j = 0; j < 2; ++j) {
             const int z = z0 + j;
@@ -598,43 +752,34 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
         SF_UNROLL
         for (int j = 0; j < 2; ++j) {
             SF_UNROLL
-            for (int c = 0; c < 5; ++c) gv[j][c] = 0u;
-            if (act[j]) {
-                gv[j][0] = SF_G(cell[j]);
-                SF_UNROLL
-                for (int i1 = 0; i1 < 4; ++i1) gv[j][1 + i1] = SF_G(sf_step_cell(cell[j], i1));
-            }
+            for (int i1 = 0; i1 < 4; ++i1) gv[j][i1] = act[j] ? (uint32_t)SF_G(sf_step_cell(cell[j], i1)) : 0u;
         }
         SF_UNROLL
         for (int j = 0; j < 2; ++j) {
             const int z = z0 + j;
-            bool go = act[j] && e.on && !(gv[j][0] & C_S2);
+            bool go = act[j] && e.on && !sf_flagged(d, t, env, cell[j]);
             bool wander = false;
             if (go) {
-                bool adjacent = false;
+                uint32_t humans = 0; /* directions in which a human stands */
                 SF_UNROLL
-                for (int i1 = 0; i1 < 4; ++i1) {
-                    uint32_t gn = gv[j][1 + i1];
-                    if (gn & C_S0) {
-                        adjacent = true;
-                        if (!(gn & C_S2) && e.on) {
-                            int b = sf_alloc_bullet(k, e);
-                            if (b >= 0) {
-                                int nc = sf_step_cell(cell[j], i1);
-                                int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
-                                sf_place_bullet(d, env, e, b, nc, gn, i1, 1, -1, md > 0 ? md : 0, 0);
-                                if (sf_is_exit(t, nc, gn)) e.watch = true;
-                                if (j == 0) { /* forward the new s[2] to the second zombie's copy */
-                                    if (cell[1] == nc) gv[1][0] = gn | C_S2;
-                                    SF_UNROLL
-                                    for (int c = 0; c < 4; ++c)
-                                        if (sf_step_cell(cell[1], c) == nc) gv[1][1 + c] = gn | C_S2;
-                                }
-                            }
+                for (int i1 = 0; i1 < 4; ++i1)
+                    if (gv[j][i1] & C_S0) humans |= 1u << i1;
+                wander = humans == 0u;
+                SF_NO_UNROLL
+                for (int i1 = 0; i1 < 4; ++i1) { /* rare: one copy of the punch, not four */
+                    if (!((humans >> i1) & 1u)) continue;
+                    const int nc = sf_step_cell(cell[j], i1);
+                    /* only a human that carries no bullet flag yet is punched: raising the flag tells */
+                    const uint32_t fl = e.on ? sf_flag_cell(d, t, env, nc) : 0u;
+                    if (fl & SF_FLAG_NEW) {
+                        int b = sf_alloc_bullet(k, e);
+                        if (b >= 0) {
+                            int md = SF_AT(d.z_mind, z); /* Zombie::punch, Character.hpp:838-844 */
+                            sf_write_bullet(d, env, b, nc, i1, 1, -1, md > 0 ? md : 0, 0, fl);
                         }
                     }
                 }
-                wander = !adjacent && e.on;
+                wander = wander && e.on;
             }
             /* one draw site: stage 0 = "stay put?" (rand()%5 < 2), stages 1, 2 = the two tries */
             int stage = wander ? 0 : 3;
@@ -647,19 +792,18 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
                     } else {
                         int i2 = r % 4;
                         int nc = sf_step_cell(cell[j], i2);
-                        uint32_t gn = i2 == 0 ? gv[j][1] : i2 == 1 ? gv[j][2] : i2 == 2 ? gv[j][3] : gv[j][4];
+                        uint32_t gn = i2 == 0 ? gv[j][0] : i2 == 1 ? gv[j][1] : i2 == 2 ? gv[j][2] : gv[j][3];
                         stage = stage == 1 ? 2 : 3;
-                        if (sf_showit(t.smap[nc], gn) == SH_DOT) {
-                            uint32_t vnew = C_S1 | (uint32_t)z, vold = gv[j][0] & ~(C_S1 | C_OCC);
+                        if (sf_showit(t.smap[nc], gn, false) == SH_DOT && !sf_flagged(d, t, env, nc)) {
+                            uint32_t vnew = C_S1 | (uint32_t)z;
                             SF_G(nc) = (uint16_t)vnew;
-                            SF_G(cell[j]) = (uint16_t)vold;
+                            SF_G(cell[j]) = (uint16_t)0u;
                             SF_AT(d.z_pos, z) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc);
                             if (j == 0) {
-                                if (cell[1] == nc) gv[1][0] = vnew;
                                 SF_UNROLL
                                 for (int c = 0; c < 4; ++c) {
-                                    if (sf_step_cell(cell[1], c) == nc) gv[1][1 + c] = vnew;
-                                    if (sf_step_cell(cell[1], c) == cell[0]) gv[1][1 + c] = vold;
+                                    if (sf_step_cell(cell[1], c) == nc) gv[1][c] = vnew;
+                                    if (sf_step_cell(cell[1], c) == cell[0]) gv[1][c] = 0u;
                                 }
                             }
                             stage = 3;
@@ -672,16 +816,17 @@ SF_FN void sf_zombie_action(const SfDev &d, const SfConst &k, const SfTabs &t, i
     }
 }
 
-/* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates.  Four exits
- * per round so that their cells load together; exits are distinct cells, so the rounds need no
+/* portal_damage, gameplay.hpp:1279-1297: an exit that does not print 'O' radiates -- one that
+ * carries a bullet flag (the table), or on which somebody stands (the overlay).  Four exits per
+ * round so that their cells load together; exits are distinct cells, so the rounds need no
  * forwarding. */
-SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
+SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
-    /* e.watch: whoever puts a human or a bullet on an exit cell raises it (zombies never enter
-     * one); an arena whose flag is down reads none of its exits, and the flag comes down again
-     * when a pass finds every exit free */
+    /* e.watch: whoever puts a human on an exit cell raises it (zombies never enter one); an arena
+     * whose flag is down reads none of its exits' cells, and the flag comes down again when a
+     * pass finds nobody on any exit */
     const bool look = e.on && e.watch;
-    const int hi = SF_WARP_MAX(look ? m2_highest(e.mp) : -1);
+    const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mp) : -1);
     bool any = false;
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
@@ -689,18 +834,22 @@ SF_FN void sf_portal_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e)
         uint32_t g[4];
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
-            lv[j] = look && i0 + j <= hi && m2_test(e.mp, i0 + j);
+            lv[j] = e.on && i0 + j <= hi && m2_test(e.mp, i0 + j);
             cell[j] = lv[j] ? sf_exit_cell(d, k, env, i0 + j) : 0;
         }
         SF_UNROLL
-        for (int j = 0; j < 4; ++j) g[j] = lv[j] ? (uint32_t)SF_G(cell[j]) : 0u;
-        SF_UNROLL
-        for (int j = 0; j < 4; ++j) {
-            if (lv[j] && (g[j] & (C_S0 | C_S1 | C_S2))) {
-                any = true;
-                if (e.on) {
+        for (int j = 0; j < 4; ++j) g[j] = (lv[j] && look) ? (uint32_t)SF_G(cell[j]) : 0u;
+        SF_NO_UNROLL
+        for (int j = 0; j < 4; ++j) { /* one copy of the look-up and the placement, not four */
+            const bool lvj = j == 0 ? lv[0] : j == 1 ? lv[1] : j == 2 ? lv[2] : lv[3];
+            const int cj = j == 0 ? cell[0] : j == 1 ? cell[1] : j == 2 ? cell[2] : cell[3];
+            const uint32_t gj = j == 0 ? g[0] : j == 1 ? g[1] : j == 2 ? g[2] : g[3];
+            if (lvj) {
+                const bool stood_on = gj & (C_S0 | C_S1);
+                any = any || stood_on;
+                if (e.on && (stood_on || sf_flagged(d, t, env, cj))) {
                     int b = sf_alloc_bullet(k, e);
-                    if (b >= 0) sf_place_bullet(d, env, e, b, cell[j], g[j], 2, 1, -1, 20, -10);
+                    if (b >= 0) sf_place_bullet(d, t, env, e, b, cj, 2, 1, -1, 20, -10);
                 }
             }
         }
@@ -745,8 +894,7 @@ SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int 
     int hp = SF_AT(d.h_hp, h) - dmg; /* Character::hit, Character.hpp:242-246 */
     SF_AT(d.h_hp, h) = hp;
     SF_AT(d.h_mind, h) += eff;
-    g &= ~C_S2;
-    m2_clear(e.mb, b);
+    m2_clear(e.mb, b); /* with its owner the cell's bullet flag is gone */
     uint32_t team_h = SF_AT(d.h_sel, h) & HS_TEAM;
     uint32_t team_o = owner >= 0 ? (SF_AT(d.h_sel, owner) & HS_TEAM) : 0u;
     uint32_t team_me = SF_AT(d.h_sel, 0) & HS_TEAM;
@@ -757,7 +905,7 @@ SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int 
     if (hp <= 0) {
         e.mh &= ~(1ull << h);
         if (h != 0) {
-            g &= ~(C_S0 | C_OCC);
+            SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
             SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT); /* deleteAgent, :648-649 */
         }
         if (owner >= 0 && team_o == team_me && team_h != team_me) {
@@ -766,7 +914,6 @@ SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int 
         }
         if (owner >= 0 && team_h != team_o) SF_AT(d.h_kills, owner) += 1;
     }
-    SF_G(cell) = (uint16_t)g;
 }
 
 /* zombie_damage, gameplay.hpp:574-598 */
@@ -777,7 +924,6 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
     int hp = SF_AT(d.z_hp, z) - dmg;
     SF_AT(d.z_hp, z) = hp;
     SF_AT(d.z_mind, z) += eff;
-    g &= ~C_S2;
     m2_clear(e.mb, b);
     if (owner >= 0) {
         SF_AT(d.h_dmg, owner) += dmg;
@@ -785,7 +931,7 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
     }
     if (hp <= 0) {
         m2_clear(e.mz, z);
-        g &= ~(C_S1 | C_OCC);
+        SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
         if (owner >= 0 && (SF_AT(d.h_sel, owner) & HS_TEAM) == (SF_AT(d.h_sel, 0) & HS_TEAM)) {
             int pts = 500 + 250 * (int)(SF_AT(d.z_pos, z) >> POS_HI_SHIFT);
             e.tkills += 1, e.loot += pts / 10;
@@ -793,7 +939,6 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
         }
         if (owner >= 0) SF_AT(d.h_kills, owner) += 1;
     }
-    SF_G(cell) = (uint16_t)g;
 }
 
 /* update_tmp + hit_human + hit_zombie, gameplay.hpp:1343-1381, 600-609, 636-652, in ONE walk over
@@ -807,11 +952,15 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
  * cell; a set s[2] always has exactly one owning bullet, so walking the owning bullets and
  * looking at who stands in their cell visits the same (victim, bullet) pairs, which are
  * independent of each other (distinct victims, distinct bullets, credits are sums).
- * Finally every owning bullet that hit nothing clears s[2] of its cell here: that is the
- * themap1 snapshot of update_bull (:1061-1072, "s[2] = 0 on the current cell of every live
- * bullet"), which nothing reads in between.  After this walk no cell has s[2] set. */
-SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &e)
+ * Finally the bullet flags of all cells are dropped (the table is wiped; the BF_OWNS bits go as
+ * the bullets move on): that is the themap1 snapshot of update_bull (:1061-1072, "s[2] = 0 on the
+ * current cell of every live bullet"), which nothing reads in between.  After this walk no cell
+ * has s[2] set. */
+SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e)
 {
+#ifdef SF_DEBUG_HIST
+    if (e.on) sf_dbg_hist[sf_bt_at(t, SF_BT_SLOTS) < 255 ? sf_bt_at(t, SF_BT_SLOTS) : 255] += 1;
+#endif
     const uint64_t quitters = e.on ? (e.quit & e.mh) : 0ull; /* Hp <= 0 by '_': removed, never hit (:640-645) */
     e.quit = 0;
     const bool built_any = e.ntemp != 0;
@@ -856,11 +1005,14 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
         for (int j = 0; j < 4; ++j) {
             if (lv[j]) {
                 const int b = b0 + j;
+                if ((meta[j] & (BF_OWNS | BF_SPILL)) == (BF_OWNS | BF_SPILL)) { /* its flag is in the overlay: take it down */
+                    g[j] &= ~C_S2;
+                    SF_G(cell[j]) = (uint16_t)g[j];
+                }
                 uint32_t kind = (g[j] >> C_KIND_SHIFT) & 7u;
                 if (built_any && (kind == K_BLOCK || (kind == K_ENTRANCE && !(g[j] & (C_S0 | C_S1))))) {
                     int q = sf_built_slot(d, env, e, cell[j], g[j]);
                     SF_T(d.t_dmg, q) += SF_AT(d.b_dmg, b);
-                    SF_G(cell[j]) = (uint16_t)(SF_G(cell[j]) & ~C_S2);
                     m2_clear(e.mb, b);
                     if (n_hit == 0) hc0 = cell[j];
                     else if (n_hit == 1) hc1 = cell[j];
@@ -873,14 +1025,13 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
                         sf_human_damage(d, env, e, occ, b, cell[j], g[j], meta[j]);
                     } else if (g[j] & C_S1) {
                         sf_zombie_damage(d, env, e, occ, b, cell[j], g[j], meta[j]);
-                    } else if (g[j] & C_S2) {
-                        SF_G(cell[j]) = (uint16_t)(g[j] & ~C_S2);
                     }
                 }
             }
         }
         SF_SYNCWARP();
     }
+    sf_bt_wipe(t);
     /* a limit can only be crossed by an absorption of this very call (while a human hides an
      * entrance nothing is absorbed, :1349), so only the cells touched above need the test */
     if (n_hit > 4) {
@@ -912,8 +1063,11 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, int env, SfEnv &
 /* update_bull, gameplay.hpp:1059-1100, plus the harness's out-of-bounds guard.  The snapshot
  * half (s[2] cleared under every live bullet) was done by sf_resolve_bullets; here the bullets
  * move, walked in the REVERSE of the reference's order so that the first bullet to reach a cell
- * is the reference's last writer of it.  Four bullets per round (positions, then the cells
- * ahead, load together); a newly set s[2] is forwarded to the later bullets of the round. */
+ * is the reference's last writer of it.  Whether a bullet may enter the cell ahead is decided by
+ * the static map alone, except on a staircase (which lets a bullet in only while somebody stands
+ * on it): a player-built block or entrance prints '#' / '^' but is "built" and takes the bullet,
+ * so the cell itself is read for staircases only.  The flag raised at the new cell goes into the
+ * table (empty since sf_resolve_bullets): a cell found there already has its last writer. */
 SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
 {
     const int hi = SF_WARP_MAX(e.on ? m2_highest(e.mb) : -1);
@@ -934,13 +1088,13 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
     for (int i0 = 0; i0 <= hi; i0 += 4) {
         bool lv[4];
         int b[4], nc[4];
-        uint32_t pw[4], meta[4], gn[4];
+        uint32_t pw[4], meta[4], gn[4], st[4];
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
             b[j] = r ? hi - (i0 + j) : i0 + j;
             lv[j] = i0 + j <= hi && (((b[j] < 64 ? live0 : live1) >> (b[j] & 63)) & 1);
             pw[j] = pw_n[j];
-            meta[j] = meta_n[j] & ~BF_OWNS;
+            meta[j] = meta_n[j] & ~(BF_OWNS | BF_SPILL);
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
@@ -961,23 +1115,19 @@ SF_FN void sf_update_bull(const SfDev &d, const SfTabs &t, int env, SfEnv &e)
                 m2_clear(e.mb, b[j]);
                 lv[j] = false;
             }
-            gn[j] = lv[j] ? (uint32_t)SF_G(nc[j]) : 0u;
+            st[j] = lv[j] ? (uint32_t)t.smap[nc[j]] : 0u;
+            gn[j] = (st[j] & (M_UP | M_DOWN)) ? (uint32_t)SF_G(nc[j]) : 0u;
         }
         SF_UNROLL
         for (int j = 0; j < 4; ++j) {
             if (lv[j]) {
-                int sit = sf_showit(t.smap[nc[j]], gn[j]);
-                bool built = ((gn[j] >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
-                if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
+                /* showit() is neither '#' nor '^' / 'v', or the cell is player-built (:1080-1083) */
+                if (!(st[j] & M_WALL) && (!(st[j] & (M_UP | M_DOWN)) || (gn[j] & (C_S0 | C_S1)))) {
                     uint32_t m = meta[j];
-                    if (!(gn[j] & C_S2)) m |= BF_OWNS;
-                    SF_G(nc[j]) = (uint16_t)(gn[j] | C_S2);
-                    if (sf_is_exit(t, nc[j], gn[j])) e.watch = true;
+                    const uint32_t fl = sf_flag_cell(d, t, env, nc[j]);
+                    if (fl & SF_FLAG_NEW) m |= BF_OWNS | (fl & BF_SPILL);
                     SF_AT(d.b_pw, b[j]) = (uint16_t)((pw[j] & ~POS_CELL) | (uint32_t)nc[j]);
                     SF_AT(d.b_meta, b[j]) = m + 0x100u;
-                    SF_UNROLL
-                    for (int jj = j + 1; jj < 4; ++jj)
-                        if (lv[jj] && nc[jj] == nc[j]) gn[jj] |= C_S2;
                 } else {
                     m2_clear(e.mb, b[j]);
                 }
@@ -1051,7 +1201,11 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
        (HS_ON_ENT); a human that stays put stands on nothing it could claim or enter */
     bool have_g = walks || (sel & HS_ON_ENT);
     uint32_t g = have_g ? (uint32_t)SF_G(cell) : 0u;
-    uint32_t gn = inb ? (uint32_t)SF_G(nc) : 0u;
+    /* the cell acted on: a punch / shot / throw is stopped by the static map alone, except on a
+       staircase (free only while somebody stands on it; see sf_update_bull) */
+    const uint32_t stn = inb ? (uint32_t)t.smap[nc] : 0u;
+    const bool fires = c == 'z' || c == 'x';
+    uint32_t gn = (inb && (!fires || (stn & (M_UP | M_DOWN)))) ? (uint32_t)SF_G(nc) : 0u;
     int st = uses_kit ? SF_AT(d.h_stam, h) : 0;
     int md = uses_kit ? SF_AT(d.h_mind, h) : 0;
     const int vec = (int)((sel >> HS_VEC_SHIFT) & 3u) - 1, ind = (int)((sel >> HS_IND_SHIFT) & 15u) - 1;
@@ -1059,7 +1213,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         SF_AT(d.h_hp, h) = 0;
         e.quit |= 1ull << h;
     } else if (c == '[' || c == ']') {
-        if (inb && sf_showit(t.smap[nc], gn) == SH_DOT) {
+        if (inb && sf_showit(stn, gn, false) == SH_DOT && !sf_flagged(d, t, env, nc)) {
             uint32_t bp = SF_AT(d.h_bp, h);
             uint32_t blocks = bp & 0xFFu, portals = (bp >> 8) & 0xFFu, pend = (bp >> 16) & 0xFFu;
             if (c == '[') {
@@ -1088,8 +1242,10 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         SF_AT(d.h_pw, h) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
     } else if (walks) {
         if (inb) {
-            int sit = sf_showit(t.smap[nc], gn);
-            if (sit == SH_CHEST || sit == SH_UP || sit == SH_DOWN || sit == SH_DOT || sit == SH_BULLET) {
+            /* '*' hides a chest, an exit or the floor: only for the exit does the flag matter */
+            int sit = sf_showit(stn, gn, false);
+            if (sit == SH_CHEST || sit == SH_UP || sit == SH_DOWN || sit == SH_DOT ||
+                (sit == SH_EXIT && sf_flagged(d, t, env, nc))) {
                 gn = (gn & ~C_OCC) | C_S0 | (uint32_t)h;
                 SF_G(nc) = (uint16_t)gn;
                 if (sf_is_exit(t, nc, gn)) e.watch = true; /* an exit under a bullet prints '*' */
@@ -1148,14 +1304,11 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
                 }
             }
             if (can) {
-                int sit = sf_showit(t.smap[nc], gn);
-                bool built = ((gn >> C_KIND_SHIFT) & 7u) >= K_BLOCK;
-                if ((sit != SH_WALL && sit != SH_DOWN && sit != SH_UP) || built) {
+                if (!(stn & M_WALL) && (!(stn & (M_UP | M_DOWN)) || (gn & (C_S0 | C_S1)))) {
                     if (b >= k.cap_b) sf_fail_env(e, SF_OVERFLOW);
                     else {
                         m2_set(e.mb, b);
-                        sf_place_bullet(d, env, e, b, nc, gn, way0, range, h, dmg, eff);
-                        if (sf_is_exit(t, nc, gn)) e.watch = true;
+                        sf_place_bullet(d, t, env, e, b, nc, way0, range, h, dmg, eff);
                     }
                 }
             }
@@ -1188,7 +1341,7 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
         if (pidx >= 0) {
             int dc = sf_exit_cell(d, k, env, pidx);
             uint32_t gd = SF_G(dc);
-            if (sf_showit(t.smap[dc], gd) == SH_EXIT) {
+            if (sf_showit(t.smap[dc], gd, false) == SH_EXIT && !sf_flagged(d, t, env, dc)) {
                 if (!have_g) g = SF_G(cell), have_g = true;
                 gd = (gd & ~C_OCC) | C_S0 | (uint32_t)h;
                 e.watch = true;
@@ -1298,7 +1451,7 @@ SF_FN void sf_royale_place(const SfDev &d, const SfConst &k, const SfTabs &t, in
         else {
             const int cell = sf_cell_of(f, r, v % SF_COLS);
             stage = 1;
-            if (sf_showit(t.smap[cell], SF_G(cell)) == SH_DOT) {
+            if (sf_showit(t.smap[cell], SF_G(cell), false) == SH_DOT) { /* no bullets yet */
                 sf_init_human(d, env, k.players[i], i, cell, false, k.teams[i], true);
                 SF_AT(d.h_pw, i) = (uint16_t)((uint32_t)cell | ((uint32_t)way0 << POS_HI_SHIFT));
                 SF_G(cell) = (uint16_t)(C_S0 | (uint32_t)i);
@@ -1409,12 +1562,12 @@ SF_FN void sf_step_halves(const SfDev &d, const SfConst &k, const SfTabs &t, int
             SF_PHASE_SYNC(1);
             sf_zombie_action(d, k, t, env, e);
             SF_PHASE_SYNC(2);
-            sf_portal_damage(d, k, env, e);
+            sf_portal_damage(d, k, t, env, e);
         } else {
             sf_human_action(d, k, t, env, e, actions);
         }
         SF_PHASE_SYNC(3);
-        sf_resolve_bullets(d, k, env, e);
+        sf_resolve_bullets(d, k, t, env, e);
         if (e.on) e.frame += 1;
         SF_PHASE_SYNC(4);
         sf_update_bull(d, t, env, e);
@@ -1534,6 +1687,7 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         d.out[env] = o;
     }
     if (half != SF_HALF_B && e.on) sd.algo_bytes += sf_algo_bytes(k, e);
+    sf_bt_rebuild(d, t, env, e);
     sf_step_halves(d, k, t, env, e, actions, half == SF_HALF_B ? 1 : 0, half == SF_HALF_A ? 0 : 1);
     if (valid) {
         /* a terminal arena that is not auto-reset waits for sf_reset: report, change nothing */

@@ -122,6 +122,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
 {
     if (cfg.abi_version != SF_ABI_VERSION) return "abi_version mismatch";
     if (cfg.n_envs <= 0) return "n_envs must be positive";
+    if (cfg.env_id_base < 0) return "env_id_base must be non-negative (it seeds levels and the synthetic streams)";
     if (cfg.mode < SF_MODE_SOLO || cfg.mode > SF_MODE_ROYALE) return "unknown mode";
     if (cfg.mode == SF_MODE_ROYALE) {
         if (cfg.royale_players < 2 || cfg.royale_players > SF_MAX_PLAYERS) return "royale_players must be 2..16";

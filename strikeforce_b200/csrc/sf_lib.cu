@@ -25,9 +25,10 @@
 #ifndef SF_CTA
 #define SF_CTA 896 /* threads per CTA = arenas in flight per SM (one CTA per SM); 28 warps x 148 SMs = 4144 >= the 4096 chunks of 131072 arenas, 72 registers per thread */
 #endif
-#define SF_SMEM_EXP 131072
+#define SF_SMEM_EXP 65536 /* the first half of the exp table (sf_exp_m1) */
 #define SF_SMEM_MAP SF_TCELLS /* 9,984, a multiple of 16 */
-#define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP)
+#define SF_SMEM_BT (SF_CTA * SF_BT_ENTRIES * 2) /* the bullet-flag tables of the CTA's arenas, [entry][thread] */
+#define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP + SF_SMEM_BT) /* 161,536 B: the 164 KB carve-out, 92 KB of L1 */
 #define SF_POW_LUT_LEN (1 << 21)
 #define SF_EXPORT_CAP (1 << 18)
 
@@ -47,6 +48,9 @@ __device__ __forceinline__ void sf_stage_tables(const SfDev &d, SfTabs &t)
     t.smap = sf_smem + SF_SMEM_EXP;
     t.log_tab = d.log_tab;
     t.rng_cst = d.rng_cst, t.E = d.E;
+    /* entry i of this thread's table at [i][thread]: two neighbouring lanes share a bank, no more */
+    t.bt = reinterpret_cast<uint16_t *>(sf_smem + SF_SMEM_EXP + SF_SMEM_MAP) + threadIdx.x;
+    t.bt_stride = SF_CTA;
 }
 
 __device__ __forceinline__ void sf_flush_stats(const SfDev &d, const SfStatDelta &sd)
@@ -140,6 +144,7 @@ __device__ __forceinline__ void sf_global_tabs(const SfDev &d, SfTabs &t)
 {
     t.exp_tab = d.exp_tab, t.log_tab = d.log_tab, t.smap = d.smap;
     t.rng_cst = d.rng_cst, t.E = d.E;
+    t.bt = nullptr, t.bt_stride = 0; /* no tick runs in these kernels */
 }
 
 __global__ void sf_hash_kernel(const SfDev d, const __grid_constant__ SfConst k, uint64_t *out)
@@ -189,24 +194,43 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
 /* gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158).
  *
  * The product is 123,008 contiguous bytes per (arena, observer), almost all zeros (floor, cells
- * outside the map) -- a pure HBM-write problem.  Persistent CTAs (five per SM, so that the
- * load latency of one overlaps the stores of the others) build each observation in shared
- * memory, 8 channels (30,752 B) at a time, and hand the tile to the TMA engine with
- * cp.async.bulk (shared -> global, bulk-group completion): the stores are whole aligned lines.
+ * outside the map) -- a pure HBM-write problem whose enemy is latency: every dependent load in
+ * front of a store is time in which the CTA writes nothing.  Persistent CTAs (four per SM) build
+ * each observation in shared memory a few channels at a time and hand the tiles to the TMA engine
+ * with cp.async.bulk (shared -> global, bulk-group completion), so the stores are whole aligned
+ * lines:
  *   1. entity -> window maps for the owning bullets and player-built cells (shared memory);
- *   2. the window is classified; cells that are neither floor nor outside the map go to a
- *      work list, so the per-cell feature code runs on dense lanes (~15% of a window);
- *   3. per tile: wait until the TMA has read the tile's previous content, write the features of
- *      the listed cells (the first tile of a window first wipes the cells the window before it
- *      listed; everything else in the tile is zero and stays zero), fence to the async proxy, one
- *      thread issues the bulk store. */
+ *   2. the window is classified in one pass into STATIC cells (walls, stairs, exits with nothing on
+ *      them: their features follow from the map byte, which rides in the list entry) and DYNAMIC
+ *      cells (anything in the overlay, or a bullet flag); floor and cells outside the map are
+ *      neither, and stay zero;
+ *   3. describe() runs ONCE per dynamic cell -- all its entity loads in one round -- and the 32
+ *      transformed features go to a channel-major cache in shared memory;
+ *   4. per tile: wait until the TMA has read what the tile buffer held two tiles ago (the buffers
+ *      alternate, so the store of tile k drains while tile k+1 is written), copy the static
+ *      constants and the cached features of the listed cells into it (the first tiles of a window
+ *      first wipe the cells the window before it listed; everything else in a tile is zero and
+ *      stays zero), fence to the async proxy, one thread issues the bulk store. */
 #ifndef SF_OBS_CTA
 #define SF_OBS_CTA 128
-#define SF_OBS_CTAS_PER_SM 5
-#define SF_OBS_HALF_CH 8 /* channels per shared-memory tile (measured: 16/256/3 -> 46%, 8/128/5 -> 51% of HBM peak) */
 #endif
-#define SF_OBS_HALF_FLOATS (SF_OBS_HALF_CH * SF_OBS_CELLS) /* 7,688 floats = 30,752 B, a multiple of 16 */
-#define SF_OBS_SMEM (SF_OBS_HALF_FLOATS * 4 + 4 * 1984 + 16)
+#ifndef SF_OBS_CTAS_PER_SM
+#define SF_OBS_CTAS_PER_SM 4
+#endif
+#ifndef SF_OBS_TILE_CH
+#define SF_OBS_TILE_CH 4 /* channels per shared-memory tile */
+#endif
+#ifndef SF_OBS_NBUF
+#define SF_OBS_NBUF 2    /* tile buffers per CTA */
+#endif
+#ifndef SF_OBS_CACHE
+#define SF_OBS_CACHE 128 /* dynamic cells whose features are cached (the rest are described again per tile) */
+#endif
+#define SF_OBS_TILE_FLOATS (SF_OBS_TILE_CH * SF_OBS_CELLS) /* 4 x 961 floats = 15,376 B, a multiple of 16 */
+#define SF_OBS_PARTS (SF_OBS_CH / SF_OBS_TILE_CH)
+#define SF_OBS_LIST 992 /* uint16 entries per cell list (>= 961, keeps the arrays 16-byte aligned) */
+#define SF_OBS_SMEM (SF_OBS_NBUF * SF_OBS_TILE_FLOATS * 4 + SF_OBS_CACHE * SF_OBS_CH * 4 + 4 * SF_OBS_LIST * 2 + 16)
+static_assert(SF_OBS_CH % SF_OBS_TILE_CH == 0 && (SF_OBS_TILE_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 __device__ __forceinline__ void sf_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
 {
@@ -215,23 +239,32 @@ __device__ __forceinline__ void sf_bulk_store(void *gdst, const void *ssrc, uint
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+/* a list entry: window index (10 bits) | the low four bits of the static map byte << 10 */
+#define SF_OBS_W(entry) ((int)((entry) & 1023u))
+#define SF_OBS_ST(entry) ((uint32_t)(entry) >> 10)
+static_assert((M_WALL | M_UP | M_DOWN | M_EXIT) == 0xFu, "the static flags describe() reads ride in a list entry");
+
 __global__ void __launch_bounds__(SF_OBS_CTA, SF_OBS_CTAS_PER_SM)
 sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
                   int nsel, int n_items)
 {
-    float *tile = reinterpret_cast<float *>(sf_smem);
-    int16_t *bmap = reinterpret_cast<int16_t *>(sf_smem + SF_OBS_HALF_FLOATS * 4);
-    int16_t *tmap = bmap + 992;
-    uint16_t *work = reinterpret_cast<uint16_t *>(tmap + 992), *prev = work + 992; /* this window's list, the last one's */
-    int *count = reinterpret_cast<int *>(work + 2 * 992);
+    float *tiles = reinterpret_cast<float *>(sf_smem);
+    float *cache = tiles + SF_OBS_NBUF * SF_OBS_TILE_FLOATS; /* [channel][cached cell] */
+    int16_t *bmap = reinterpret_cast<int16_t *>(cache + SF_OBS_CACHE * SF_OBS_CH);
+    int16_t *tmap = bmap + SF_OBS_LIST;
+    /* this window's list and the last one's: static cells from the front, dynamic ones from the back */
+    uint16_t *list = reinterpret_cast<uint16_t *>(tmap + SF_OBS_LIST), *prev = list + SF_OBS_LIST;
+    int *count = reinterpret_cast<int *>(list + 2 * SF_OBS_LIST); /* [0] static, [1] dynamic */
     SfTabs t;
     sf_global_tabs(d, t);
     uint32_t fb = 0;
-    int n_prev = 0;
-    /* the tile is zero outside the listed cells at all times: it is cleared once, and a window only
-       wipes what the window before it wrote */
-    for (int i = threadIdx.x; i < SF_OBS_HALF_FLOATS / 4; i += SF_OBS_CTA)
-        reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float lut_1000 = sf_obs_transform(d, 1000, &fb), lut_20 = sf_obs_transform(d, 20, &fb), lut_10 = sf_obs_transform(d, 10, &fb);
+    int ps_stat = 0, ps_dyn = 0; /* the last window's counts */
+    uint32_t tile_no = 0;        /* tiles stored so far by this CTA: buffer = tile_no % SF_OBS_NBUF */
+    /* the tiles are zero outside the listed cells at all times: they are cleared once, and a window
+       only wipes what the window before it wrote */
+    for (int i = threadIdx.x; i < SF_OBS_NBUF * SF_OBS_TILE_FLOATS / 4; i += SF_OBS_CTA)
+        reinterpret_cast<float4 *>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int env = item / nsel;
         uint32_t m = agent_mask;
@@ -252,9 +285,19 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         sf_tcell_decode(vcell, &vf, &vr, &vc);
         const int r0 = vr - SF_OBS_R, c0 = vc - SF_OBS_R;
         for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
-        if (threadIdx.x == 0) *count = 0;
+        if (threadIdx.x < 2) count[threadIdx.x] = 0;
         __syncthreads();
         if (observer) {
+            /* the loads of a thread's eight window cells are issued first: they are in flight while
+               the entity maps are filled */
+            constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
+            uint32_t cv[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int w = threadIdx.x + q * SF_OBS_CTA;
+                const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
+                cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
+            }
             for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
                 if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
                     int bf, br, bc;
@@ -270,53 +313,100 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                 if (tf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
                     tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
             }
-            /* the loads of a thread's eight window cells are issued together, then classified */
-            constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
-            uint32_t cv[PER];
+            __syncthreads();
+            /* a cell that carries nothing but a bullet flag has an empty overlay word: bmap lists it */
 #pragma unroll
             for (int q = 0; q < PER; ++q) {
                 const int w = threadIdx.x + q * SF_OBS_CTA;
-                const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
-                cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
+                if (w < SF_OBS_CELLS) {
+                    const uint32_t entry = (uint32_t)w | ((cv[q] >> 16) & 0xFu) << 10;
+                    if ((cv[q] & 0xFFFFu) || bmap[w] >= 0) list[SF_OBS_LIST - 1 - atomicAdd(&count[1], 1)] = (uint16_t)entry;
+                    else if (entry >> 10) list[atomicAdd(&count[0], 1)] = (uint16_t)entry;
+                }
             }
-#pragma unroll
-            for (int q = 0; q < PER; ++q)
-                if (cv[q]) work[atomicAdd(count, 1)] = (uint16_t)(threadIdx.x + q * SF_OBS_CTA);
         }
         __syncthreads();
-        const int n_work = *count;
+        const int n_stat = count[0], n_dyn = count[1];
+        /* describe() once per dynamic cell; its 32 transformed features wait in the cache */
+        for (int i = threadIdx.x; i < n_dyn && i < SF_OBS_CACHE; i += SF_OBS_CTA) {
+            const uint32_t entry = list[SF_OBS_LIST - 1 - i];
+            const int w = SF_OBS_W(entry), cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+            int32_t f[32];
+            sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
 #pragma unroll
-        for (int part = 0; part < SF_OBS_CH / SF_OBS_HALF_CH; ++part) {
-            float *half = tile;
-            /* the TMA must have read the tile's previous content before it is overwritten */
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            for (int c = 0; c < SF_OBS_CH; ++c) cache[c * SF_OBS_CACHE + i] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
+        }
+#pragma unroll 1
+        for (int part = 0; part < SF_OBS_PARTS; ++part, ++tile_no) {
+            float *tile = tiles + (tile_no % SF_OBS_NBUF) * SF_OBS_TILE_FLOATS;
+#ifdef SF_OBS_TMA
+            /* the TMA must have read the buffer's previous content before it is overwritten; the
+               barrier also publishes the cache */
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SF_OBS_NBUF - 1) : "memory");
             __syncthreads();
-            if (part == 0) { /* the later tiles of a window overwrite exactly the cells of its first one */
-                for (int i = threadIdx.x; i < n_prev; i += SF_OBS_CTA) {
-                    const int w = prev[i];
+#endif
+            if (part < SF_OBS_NBUF) { /* the buffer last held a tile of the window before: wipe its cells
+                                         (the barrier after it also publishes the cache) */
+                for (int i = threadIdx.x; i < ps_stat + ps_dyn; i += SF_OBS_CTA) {
+                    const int w = SF_OBS_W(prev[i < ps_stat ? i : SF_OBS_LIST - 1 - (i - ps_stat)]);
 #pragma unroll
-                    for (int c = 0; c < SF_OBS_HALF_CH; ++c) half[c * SF_OBS_CELLS + w] = 0.f;
+                    for (int c = 0; c < SF_OBS_TILE_CH; ++c) tile[c * SF_OBS_CELLS + w] = 0.f;
                 }
                 __syncthreads();
             }
-            for (int i = threadIdx.x; i < n_work; i += SF_OBS_CTA) {
-                const int w = work[i];
+            for (int i = threadIdx.x; i < n_stat; i += SF_OBS_CTA) {
+                const uint32_t entry = list[i];
+                const int w = SF_OBS_W(entry);
                 int32_t f[32];
-                sf_describe_milli(d, k, t, env, e, sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN), team, bmap[w],
-                                  tmap[w], f);
-#pragma unroll
-                for (int c = 0; c < SF_OBS_HALF_CH; ++c)
-                    half[c * SF_OBS_CELLS + w] = sf_obs_transform(d, f[part * SF_OBS_HALF_CH + c], &fb);
+                sf_describe_cell(d, k, env, e, 0, SF_OBS_ST(entry), 0u, team, -1, -1, f); /* no memory access */
+                for (int c = 0; c < SF_OBS_TILE_CH; ++c) { /* a static cell's features are 1, 0.02 or 0.01 */
+                    const int32_t v = f[part * SF_OBS_TILE_CH + c];
+                    tile[c * SF_OBS_CELLS + w] = v == 0 ? 0.f : v == 1000 ? lut_1000 : v == 20 ? lut_20 : v == 10 ? lut_10
+                                                                                          : sf_obs_transform(d, v, &fb);
+                }
             }
+            for (int i = threadIdx.x; i < n_dyn; i += SF_OBS_CTA) {
+                const uint32_t entry = list[SF_OBS_LIST - 1 - i];
+                const int w = SF_OBS_W(entry);
+                if (i < SF_OBS_CACHE) {
+#pragma unroll
+                    for (int c = 0; c < SF_OBS_TILE_CH; ++c)
+                        tile[c * SF_OBS_CELLS + w] = cache[(part * SF_OBS_TILE_CH + c) * SF_OBS_CACHE + i];
+                } else { /* more dynamic cells than the cache holds: described again for every tile */
+                    const int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+                    int32_t f[32];
+                    sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
+                    for (int c = 0; c < SF_OBS_TILE_CH; ++c) {
+                        const int32_t v = f[part * SF_OBS_TILE_CH + c];
+                        tile[c * SF_OBS_CELLS + w] = v ? sf_obs_transform(d, v, &fb) : 0.f;
+                    }
+                }
+            }
+#ifdef SF_OBS_TMA
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> async proxy */
             __syncthreads();
-            if (threadIdx.x == 0) sf_bulk_store(out + part * SF_OBS_HALF_FLOATS, half, SF_OBS_HALF_FLOATS * 4);
-            static_assert((SF_OBS_HALF_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
+            if (threadIdx.x == 0) sf_bulk_store(out + part * SF_OBS_TILE_FLOATS, tile, SF_OBS_TILE_FLOATS * 4);
+#else
+            /* copy-out: whole 512-byte runs per warp, fire and forget -- a store holds no shared
+               memory once it has issued, so the bytes in flight are not bounded by the tile buffers.
+               One barrier per tile is enough: a thread that starts filling this buffer again (two
+               tiles on) has passed the barrier of the tile in between, which every thread reaches
+               only after its part of this copy-out. */
+            __syncthreads();
+            {
+                const float4 *src = reinterpret_cast<const float4 *>(tile);
+                float4 *dst = reinterpret_cast<float4 *>(out + part * SF_OBS_TILE_FLOATS);
+#pragma unroll 4
+                for (int i = threadIdx.x; i < SF_OBS_TILE_FLOATS / 4; i += SF_OBS_CTA) __stcs(dst + i, src[i]);
+            }
+#endif
         }
-        uint16_t *sw = work;
-        work = prev, prev = sw, n_prev = n_work;
+        uint16_t *sw = list;
+        list = prev, prev = sw, ps_stat = n_stat, ps_dyn = n_dyn;
     }
+#ifdef SF_OBS_TMA
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }
 
@@ -339,7 +429,7 @@ sf_rng_kernel(const SfDev d, const int64_t *tb, const int64_t *serial, int n_str
         for (; n < SF_WARM_DRAWS; ++n) sf_warm_draw(t, Lp, c, n);
         for (int j = 0; j < n_draws; ++j, ++n) {
             sf_warm_draw(t, Lp, c, n);
-            out[(size_t)j * n_streams + i] = (int32_t)(((uint32_t)t.exp_tab[Lp[8] >> 16] + 1u) & 1023u);
+            out[(size_t)j * n_streams + i] = (int32_t)((sf_exp_m1(t, 2u * (Lp[8] >> 16)) + 1u) & 1023u);
         }
     }
 }
@@ -359,6 +449,7 @@ struct sf_handle {
     int32_t *d_ids = nullptr;
     int64_t *d_tb = nullptr, *d_serial = nullptr;
     int device = 0, n_sm = 0;
+    bool between_halves = false; /* sf_step_a has run, sf_step_b has not: the P2 observation point */
     long long launches = 0;
     std::string err;
 };
@@ -380,6 +471,18 @@ static int sf_fail(sf_handle *h, int code, const std::string &msg)
                            std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
 
+/* A handle lives on the device that was current in sf_create; every entry point runs there,
+ * whatever device the calling thread has current, and puts the caller's device back. */
+struct SfDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit SfDeviceGuard(const sf_handle *h);
+    ~SfDeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static int sf_require_device(sf_handle *h)
 {
     int n = 0;
@@ -389,6 +492,11 @@ static int sf_require_device(sf_handle *h)
         return sf_fail(h, SF_ERR_NO_DEVICE, "no usable CUDA device: strikeforce_b200 has no CPU path");
     }
     return SF_OK;
+}
+
+SfDeviceGuard::SfDeviceGuard(const sf_handle *h)
+{
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
 }
 
 namespace {
@@ -483,7 +591,7 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     }
     if (smem_optin < SF_SMEM_BYTES) {
         delete h;
-        return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 141,056 B)");
+        return sf_fail(nullptr, SF_ERR_UNSUPPORTED, "device offers too little shared memory per block (need 161,536 B)");
     }
     Carver sizer;
     carve(sizer, *h);
@@ -540,8 +648,11 @@ int sf_create(const sf_config *cfg, sf_handle **out)
 int sf_destroy(sf_handle *h)
 {
     if (!h) return SF_ERR_ARG;
-    cudaDeviceSynchronize();
-    cudaFree(h->arena);
+    {
+        SfDeviceGuard guard(h);
+        cudaDeviceSynchronize();
+        cudaFree(h->arena);
+    }
     delete h;
     return SF_OK;
 }
@@ -549,6 +660,7 @@ int sf_destroy(sf_handle *h)
 int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb, const int64_t *serial, void *stream)
 {
     if (!h) return SF_ERR_ARG;
+    SfDeviceGuard guard(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!env_ids) n = h->d.n_envs;
     if (n <= 0 || n > h->d.n_envs) return sf_fail(h, SF_ERR_ARG, "sf_reset: bad arena count");
@@ -566,6 +678,7 @@ int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb,
     }
     int rc = sf_launch_reset(h, env_ids ? h->d_ids : nullptr, n, tb ? h->d_tb : nullptr, tb ? h->d_serial : nullptr, s);
     if (rc) return rc;
+    h->between_halves = false;
     /* the staging buffers are reused by the next call */
     SF_CUDA(h, cudaStreamSynchronize(s));
     return SF_OK;
@@ -573,6 +686,11 @@ int sf_reset(sf_handle *h, const int32_t *env_ids, int32_t n, const int64_t *tb,
 
 static int sf_launch_step(sf_handle *h, int half, const uint8_t *d_actions, cudaStream_t s)
 {
+    SfDeviceGuard guard(h);
+    if ((half == SF_HALF_B) != h->between_halves)
+        return sf_fail(h, SF_ERR_ARG, half == SF_HALF_B ? "sf_step_b: no sf_step_a before it"
+                                                        : "sf_step / sf_step_a: the step opened by sf_step_a is still waiting for sf_step_b");
+    h->between_halves = half == SF_HALF_A;
     int nchunks = h->d.E / 32;
     int grid = nchunks < h->n_sm ? nchunks : h->n_sm; /* one persistent CTA per SM; warps take chunks round-robin */
     if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
@@ -604,6 +722,7 @@ int sf_step_b(sf_handle *h, const uint8_t *actions, void *stream)
 int sf_step_host(sf_handle *h, const uint8_t *actions_host, sf_step_out *out_host, void *stream)
 {
     if (!h || !actions_host || !out_host) return h ? sf_fail(h, SF_ERR_ARG, "sf_step_host: null argument") : SF_ERR_ARG;
+    SfDeviceGuard guard(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     size_t na = (size_t)h->d.n_envs * (size_t)h->k.n_agents;
     /* page-locked buffers (cudaHostAlloc / cudaHostRegister) are used in place: the kernel reads each
@@ -636,6 +755,7 @@ int sf_synth_actions(sf_handle *h, uint8_t *actions, uint64_t t, const char *tab
 {
     if (!h || !actions || !table || table_len <= 0 || table_len > 256)
         return h ? sf_fail(h, SF_ERR_ARG, "sf_synth_actions: bad argument") : SF_ERR_ARG;
+    SfDeviceGuard guard(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SF_CUDA(h, cudaMemcpyAsync(h->d_table, table, (size_t)table_len, cudaMemcpyHostToDevice, s));
     int n = h->d.n_envs * h->k.n_agents;
@@ -650,6 +770,13 @@ int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, voi
 {
     if (!h || !obs) return h ? sf_fail(h, SF_ERR_ARG, "sf_observe: null buffer") : SF_ERR_ARG;
     if (phase != SF_OBS_P1 && phase != SF_OBS_P2) return sf_fail(h, SF_ERR_ARG, "sf_observe: phase must be SF_OBS_P1 or SF_OBS_P2");
+    /* the kernel describes the arena as it stands; the phase says WHERE in the step the caller claims
+       to be, and a claim that does not match the handle is an error: P2 is the point between
+       sf_step_a and sf_step_b (get_command inside human_action), P1 the loop top */
+    if ((phase == SF_OBS_P2) != h->between_halves)
+        return sf_fail(h, SF_ERR_ARG, phase == SF_OBS_P2 ? "sf_observe: SF_OBS_P2 is the point between sf_step_a and sf_step_b"
+                                                         : "sf_observe: between sf_step_a and sf_step_b the observation point is SF_OBS_P2");
+    SfDeviceGuard guard(h);
     int nsel = __builtin_popcount(agent_mask);
     if (nsel == 0) return sf_fail(h, SF_ERR_ARG, "sf_observe: empty agent mask");
     if (reinterpret_cast<uintptr_t>(obs) & 15u) return sf_fail(h, SF_ERR_ARG, "sf_observe: obs must be 16-byte aligned");
@@ -665,6 +792,7 @@ int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, voi
 int sf_get(sf_handle *h, int32_t field, void *dev_out, void *stream)
 {
     if (!h || !dev_out) return h ? sf_fail(h, SF_ERR_ARG, "sf_get: null buffer") : SF_ERR_ARG;
+    SfDeviceGuard guard(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int n = h->d.n_envs, grid = (n + 127) / 128;
     switch (field) {
@@ -695,6 +823,7 @@ int sf_export_env(sf_handle *h, int32_t env, int32_t *host_buf, int64_t *n_inout
 {
     if (!h || !host_buf || !n_inout) return h ? sf_fail(h, SF_ERR_ARG, "sf_export_env: null argument") : SF_ERR_ARG;
     if (env < 0 || env >= h->d.n_envs) return sf_fail(h, SF_ERR_ARG, "sf_export_env: arena id out of range");
+    SfDeviceGuard guard(h);
     SF_CUDA(h, cudaDeviceSynchronize());
     sf_export_kernel<<<1, 1>>>(h->d, h->k, env, h->d_export, (long)SF_EXPORT_CAP, h->d_export_n);
     h->launches += 1;
@@ -712,21 +841,26 @@ int sf_rng_stream(sf_handle *h, const int64_t *tb, const int64_t *serial, int32_
 {
     if (!h || !tb || !serial || !out_host || n_streams <= 0 || n_draws <= 0)
         return h ? sf_fail(h, SF_ERR_ARG, "sf_rng_stream: bad argument") : SF_ERR_ARG;
-    int64_t *d_tb = nullptr, *d_serial = nullptr;
-    int32_t *d_out = nullptr;
-    size_t n_out = (size_t)n_streams * (size_t)n_draws;
-    SF_CUDA(h, cudaMalloc(&d_tb, (size_t)n_streams * 8));
-    SF_CUDA(h, cudaMalloc(&d_serial, (size_t)n_streams * 8));
-    SF_CUDA(h, cudaMalloc(&d_out, n_out * 4));
-    SF_CUDA(h, cudaMemcpy(d_tb, tb, (size_t)n_streams * 8, cudaMemcpyHostToDevice));
-    SF_CUDA(h, cudaMemcpy(d_serial, serial, (size_t)n_streams * 8, cudaMemcpyHostToDevice));
+    for (int32_t i = 0; i < n_streams; ++i)
+        if (tb[i] < 0 || serial[i] < 0) return sf_fail(h, SF_ERR_ARG, "sf_rng_stream: seeds must be non-negative");
+    SfDeviceGuard guard(h);
+    /* one allocation for the three buffers, released on every path */
+    const size_t n_out = (size_t)n_streams * (size_t)n_draws, seeds = (size_t)n_streams * 8;
+    struct Scratch {
+        void *p = nullptr;
+        ~Scratch() { cudaFree(p); }
+    } scratch;
+    SF_CUDA(h, cudaMalloc(&scratch.p, 2 * seeds + n_out * 4));
+    int64_t *d_tb = static_cast<int64_t *>(scratch.p), *d_serial = d_tb + n_streams;
+    int32_t *d_out = reinterpret_cast<int32_t *>(d_serial + n_streams);
+    SF_CUDA(h, cudaMemcpy(d_tb, tb, seeds, cudaMemcpyHostToDevice));
+    SF_CUDA(h, cudaMemcpy(d_serial, serial, seeds, cudaMemcpyHostToDevice));
     int grid = (n_streams + SF_CTA - 1) / SF_CTA;
     if (grid > h->n_sm) grid = h->n_sm;
     sf_rng_kernel<<<grid, SF_CTA, SF_SMEM_BYTES>>>(h->d, d_tb, d_serial, n_streams, n_draws, d_out);
     h->launches += 1;
     SF_CUDA(h, cudaGetLastError());
     SF_CUDA(h, cudaMemcpy(out_host, d_out, n_out * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_tb), cudaFree(d_serial), cudaFree(d_out);
     return SF_OK;
 }
 

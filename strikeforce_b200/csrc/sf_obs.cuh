@@ -48,18 +48,18 @@ SF_FN void sf_damage_effect(const SfDev &d, const SfConst &k, int env, const SfE
     *eff = 0;
 }
 
-/* describe(cell, player), Custom.hpp:29-135, in thousandths.  cell < 0 is the all-zero cell
- * `nd` used outside the map (:147-148).  bidx / tq: the owning bullet of the cell and its
- * player-built record if the caller already knows them, else -2 to look them up here. */
-SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, int env, const SfEnv &e, int cell,
-                             uint32_t viewer_team, int bidx, int tq, int32_t f[32])
+/* describe(cell, player), Custom.hpp:29-135, in thousandths, from the cell's static byte `st` and
+ * overlay word `g`.  bidx / tq: the owning bullet of the cell and its player-built record if the
+ * caller already knows them, else -2 to look them up here.  With g == 0 and bidx == -1 (a cell
+ * that holds nothing dynamic) this touches no memory at all. */
+SF_FN void sf_describe_cell(const SfDev &d, const SfConst &k, int env, const SfEnv &e, int cell, uint32_t st, uint32_t g,
+                            uint32_t viewer_team, int bidx, int tq, int32_t f[32])
 {
     SF_UNROLL
     for (int i = 0; i < 32; ++i) f[i] = 0;
-    if (cell < 0) return;
-    uint32_t st = t.smap[cell], g = SF_G(cell);
     uint32_t kind = (g >> C_KIND_SHIFT) & 7u;
-    bool s0 = g & C_S0, s1 = g & C_S1, s2 = g & C_S2;
+    if (bidx == -2) bidx = sf_owner_scan(d, env, e, cell, -1);
+    bool s0 = g & C_S0, s1 = g & C_S1, s2 = bidx >= 0; /* the bullet flag lives in the bullet list */
     bool s3 = (st & M_WALL) || kind == K_BLOCK;
     bool s4 = kind >= K_CHEST0 && kind < K_BLOCK;
     bool s5 = (st & M_UP) || kind == K_ENTRANCE, s6 = st & M_DOWN;
@@ -103,13 +103,8 @@ SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, 
         f[20] = f[21] = f[22] = f[23] = 10; /* 0.01 */
         f[24] = SF_AT(d.z_mind, occ);
     } else if (s2) {
-        if (bidx == -2) {
-            bidx = -1;
-            for (int b = m2_next(e.mb, 0); b >= 0; b = m2_next(e.mb, b + 1))
-                if ((SF_AT(d.b_meta, b) & BF_OWNS) && (int)(SF_AT(d.b_pw, b) & POS_CELL) == cell) bidx = b;
-        }
         f[19] = 1000;
-        if (bidx >= 0) {
+        {
             uint32_t meta = SF_AT(d.b_meta, bidx);
             int range = (int)(meta & 0xFFu), trav = (int)((meta >> 8) & 0xFFu);
             f[20 + (int)(SF_AT(d.b_pw, bidx) >> POS_HI_SHIFT)] = 10 * (range - trav); /* (range - dist) / 100.0 */
@@ -123,6 +118,19 @@ SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, 
         f[27] = c.stamina, f[28] = c.effect, f[29] = c.hp;
     }
     if (s0) f[30] = SF_AT(d.h_dmg, occ), f[31] = -SF_AT(d.h_eff, occ);
+}
+
+/* describe() of map cell `cell`; cell < 0 is the all-zero cell `nd` used outside the map
+ * (Custom.hpp:147-148) */
+SF_FN void sf_describe_milli(const SfDev &d, const SfConst &k, const SfTabs &t, int env, const SfEnv &e, int cell,
+                             uint32_t viewer_team, int bidx, int tq, int32_t f[32])
+{
+    if (cell < 0) {
+        SF_UNROLL
+        for (int i = 0; i < 32; ++i) f[i] = 0;
+        return;
+    }
+    sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), viewer_team, bidx, tq, f);
 }
 
 /* beyond the host-built table: the device's pow (counted by the caller; it may differ from

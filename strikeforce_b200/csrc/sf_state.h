@@ -16,15 +16,18 @@
  * Cell overlay word (uint16), the dynamic part of `struct node` (gameplay.hpp:237-243):
  *   bits 0-7   slot of the human / zombie standing here (valid under S0 / S1; a cell never
  *              holds both: humans enter '?^v.X*' cells only, zombies '.' only, :750, :682)
- *   bit  8     s[0] human     bit 9  s[1] zombie     bit 10  s[2] bullet flag
+ *   bit  8     s[0] human     bit 9  s[1] zombie     (bit 10: s[2], the bullet flag, is a
+ *              property of the bullet list and is kept here only when an arena's flag table
+ *              overflows, see "the bullet flag" in sf_core.cuh; no rule reads it from a cell word)
  *   bits 11-13 kind: 0 none, 1-4 chest of type kind-1 (s[4] + cons), 5 player-built block
  *              (s[3]+s[10]), 6 player-built entrance (s[5]+s[10]), 7 player-built exit
  *              (s[7]+s[10]).  Chests and built objects both need a '.' cell, so they never
  *              coincide (:536, :706).
  *   bits 14-15 with bits 0-7: on a player-built cell nobody stands on, a validated hint of the
  *              slot of its record in the built list (sf_built_slot).
- * The reference's last-writer bullet pointer (node::bullet, trusted only under s[2]) is the
- * BF_OWNS bit of exactly one live bullet standing in that cell ("last writer").
+ * The reference's bullet flag s[2] and its last-writer pointer (node::bullet, trusted only under
+ * s[2]) are the BF_OWNS bit of exactly one live bullet standing in that cell ("last
+ * writer"); no cell word changes when a bullet moves.
  */
 #ifndef SF_STATE_H
 #define SF_STATE_H
@@ -64,7 +67,7 @@ SF_HDI void sf_tcell_decode(int t, int *f, int *r, int *c)
 #define C_OCC 0x00FFu
 #define C_S0 0x0100u
 #define C_S1 0x0200u
-#define C_S2 0x0400u
+#define C_S2 0x0400u /* only for the flags an arena's table had no room for (sf_core.cuh, "the bullet flag") */
 #define C_KIND_SHIFT 11
 #define C_KIND (7u << C_KIND_SHIFT)
 enum { K_NONE = 0, K_CHEST0 = 1, K_BLOCK = 5, K_ENTRANCE = 6, K_EXIT = 7 };
@@ -94,8 +97,9 @@ enum { SH_WALL, SH_HUMAN, SH_ZOMBIE, SH_UP, SH_DOWN, SH_BULLET, SH_CHEST, SH_EXI
 /* position words: cell id in bits 0-13, (way - 1) or `super` in bits 14-15 */
 #define POS_CELL 0x3FFFu
 #define POS_HI_SHIFT 14
-/* bullet word b_meta: range | travelled << 8 | (owner + 1) << 16 | BF_OWNS */
+/* bullet word b_meta: range | travelled << 8 | (owner + 1) << 16 | BF_OWNS | BF_SPILL */
 #define BF_OWNS 0x01000000u
+#define BF_SPILL 0x02000000u /* with BF_OWNS: the flag it owns is kept in the overlay (C_S2), not in the table */
 
 /* hard limits of this layout (sf_create validates the configured caps against them) */
 #define SF_LIM_HUMANS 64

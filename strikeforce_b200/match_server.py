@@ -35,8 +35,14 @@ from __future__ import annotations
 import socket
 
 
+TICK_TIMEOUT = 0.5   # SO_RCVTIMEO of the match sockets, server.cpp:265-279
+LOBBY_TIMEOUT = 5.0  # a connection that never sends its password must not hold the lobby
+
+
 def recv_cstr(sock, limit=4096):
-    """my_recv, server.cpp:62-75: bytes up to the terminating NUL; None when the peer is gone."""
+    """my_recv, server.cpp:62-75: bytes up to the terminating NUL; None when the peer is gone --
+    closed, reset, or silent for longer than the socket's timeout (socket.timeout is an OSError:
+    the reference treats a receive time-out exactly like a dead connection and plays '_')."""
     out = bytearray()
     while len(out) < limit:
         try:
@@ -55,11 +61,21 @@ def send_cstr(sock, payload: bytes):
     sock.sendall(payload + b"\0")
 
 
+def try_send(sock, payload: bytes):
+    """sendall that reports a dead peer instead of raising (BrokenPipe / ConnectionReset / time-out)"""
+    try:
+        sock.sendall(payload)
+        return True
+    except OSError:
+        return False
+
+
 class MatchHost:
     """One match.  ``teams[i]`` = team of seat i; ``local_seats`` = {seat: sheet text} for the seats the
     host plays itself; the other seats are taken by connecting clients in the order they connect."""
 
-    def __init__(self, teams, password, tb, serial, local_seats=None):
+    def __init__(self, teams, password, tb, serial, local_seats=None, tick_timeout=TICK_TIMEOUT,
+                 lobby_timeout=LOBBY_TIMEOUT):
         self.teams = list(teams)
         self.n = len(self.teams)
         self.password = password.encode() if isinstance(password, str) else bytes(password)
@@ -70,6 +86,7 @@ class MatchHost:
         self.announce = [False] * self.n
         self.command = [ord("+")] * self.n
         self.sheets = {}  # seat -> the sheet text every player announced
+        self.tick_timeout, self.lobby_timeout = tick_timeout, lobby_timeout
 
     # ---------------------------------------------------------------- lobby, server.cpp:196-250
     @property
@@ -82,26 +99,29 @@ class MatchHost:
             while seat not in self.socks:
                 conn, _ = listener.accept()
                 conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                conn.settimeout(self.lobby_timeout)
                 pw = recv_cstr(conn, 32)
-                if pw == self.password:
-                    send_cstr(conn, b"A")
+                if pw == self.password and try_send(conn, b"A\0"):
                     self.socks[seat] = conn
-                else:
-                    send_cstr(conn, b"R")
+                else:  # wrong password, silence, or gone before the answer: the seat stays free
+                    try_send(conn, b"R\0")
                     conn.close()
 
     def handshake(self):
+        """Seeds, roster and sheets.  A peer that drops here keeps its seat (the roster has gone out)
+        and leaves the match on the first tick, as a client that dies right after the lobby does."""
         for s in self.socks.values():
-            send_cstr(s, b"%d %d" % (self.tb, self.serial))
+            try_send(s, b"%d %d\0" % (self.tb, self.serial))
         for i, s in self.socks.items():
-            send_cstr(s, b"%d %d %d" % (self.n, i, self.teams[i]))
+            try_send(s, b"%d %d %d\0" % (self.n, i, self.teams[i]))
         for i in range(self.n):
             info = self.local[i].encode() if i in self.local else (recv_cstr(self.socks[i], 2048) or b"")
             self.sheets[i] = info.decode("latin-1")
             for j, s in self.socks.items():
                 if j != i:
-                    send_cstr(s, info)
-                    send_cstr(s, b"%d" % self.teams[i])
+                    try_send(s, info + b"\0" + b"%d\0" % self.teams[i])
+        for s in self.socks.values():  # from here on a silent client is a gone client, server.cpp:265-279
+            s.settimeout(self.tick_timeout)
 
     # ---------------------------------------------------------------- one tick, server.cpp:77-132
     def tick(self, local_commands=None):
@@ -127,9 +147,12 @@ class MatchHost:
                     self.announce[i] = True
         for i, s in self.socks.items():
             if self.alive[i]:
-                for j in range(self.n):
-                    if (self.alive[j] or self.announce[j]) and i != j:
-                        s.sendall(bytes([self.command[j], 0]))
+                out = b"".join(bytes([self.command[j], 0]) for j in range(self.n)
+                               if (self.alive[j] or self.announce[j]) and i != j)
+                if not try_send(s, out):
+                    # the peer dropped between its command and the relay: its command of this tick
+                    # stands (every other copy has it); the next receive fails and plays its '_'
+                    pass
         row = bytes(self.command[i] if (self.alive[i] or self.announce[i] or self.command[i] == ord("~")) else ord("+")
                     for i in range(self.n))
         return row, self._result()

@@ -117,32 +117,65 @@ class AgentModel(nn.Module):
 class PolicyAgent:
     """``Agent`` of bots/bot-0.5/Agent.hpp:178-224 for a batch: ``predict`` runs the network on the
     observations of ``sf_observe`` and samples an action per row with a seeded device generator
-    (the reference samples with std::random_device, which cannot be reproduced)."""
+    (the reference samples with std::random_device, which cannot be reproduced).
 
-    def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False, chunk=0):
+    What the reference's ``predict`` does around the network is kept, per row:
+
+    * the first ``t_initial`` (= ``T_initial`` = 10, Agent.hpp:274) calls of an episode return action 0
+      without running the model (:179-180; ``cnt`` counts the calls of an ``Agent``, and a game creates a
+      fresh one);
+    * ``slowmotion=True`` is the shipped build (macros.hpp:18 defines SLOWMOTION): the action is drawn
+      from the network's distribution as it is.  ``slowmotion=False`` is the build without that macro
+      (:204-208): action 0 gets probability 0.5 and the others are scaled by ``0.5 / (1 - p0 + 1e-5)``;
+    * ``reset_rows(mask)`` is the new ``Agent`` of the next game (``reset_memory``, Modules.hpp:94-99):
+      zero GRU states, the action one-hot back on index 0, the call counter back to 0 -- call it with
+      the arenas whose ``step_out`` status is terminal (``bots.play`` does)."""
+
+    def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False, chunk=0, t_initial=10,
+                 slowmotion=True):
         self.model = model.to(device).eval()
         self.state = model.initial_state(batch, device)
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed)
         self.training = training
         self.chunk = chunk  # >0: rows per forward call (bounds the activations of very large batches)
+        self.t_initial = t_initial
+        self.slowmotion = slowmotion
+        self.calls = torch.zeros(batch, dtype=torch.int32, device=device)  # Agent::cnt per row
+
+    def _sample(self, p):
+        if not self.slowmotion:  # Agent.hpp:204-208
+            p = p.clone()
+            p[:, 1:] *= (0.5 / (1 - p[:, 0] + 1e-5)).unsqueeze(1)
+            p[:, 0] = 0.5
+        return torch.multinomial(p, 1, generator=self.gen).view(-1)
 
     @torch.no_grad()
     def predict(self, obs):
         B = obs.shape[0]
-        if not self.chunk or B <= self.chunk:
-            p, _, st = self.model(obs, self.state)
-            act = torch.multinomial(p, 1, generator=self.gen).view(-1)
-            self.state = AgentModel.with_action(st, act)
-            return act
-        act = torch.empty(B, dtype=torch.int64, device=obs.device)
-        for lo in range(0, B, self.chunk):
-            hi = min(B, lo + self.chunk)
-            p, _, st = self.model(obs[lo:hi], tuple(s[lo:hi] for s in self.state))
-            act[lo:hi] = torch.multinomial(p, 1, generator=self.gen).view(-1)
-            for dst, src in zip(self.state, AgentModel.with_action(st, act[lo:hi])):
-                dst[lo:hi] = src
+        # rows still inside their first t_initial calls answer 0 and leave the network's memory alone
+        live = self.calls >= self.t_initial
+        self.calls += (~live).to(self.calls.dtype)
+        act = torch.zeros(B, dtype=torch.int64, device=obs.device)
+        step = self.chunk if self.chunk and B > self.chunk else B
+        for lo in range(0, B, step):
+            hi = min(B, lo + step)
+            sub = tuple(s[lo:hi] for s in self.state)
+            p, _, st = self.model(obs[lo:hi], sub)
+            a = torch.where(live[lo:hi], self._sample(p), act[lo:hi])
+            keep = live[lo:hi].unsqueeze(1)
+            for dst, new, old in zip(self.state, AgentModel.with_action(st, a), sub):
+                dst[lo:hi] = torch.where(keep, new, old)
+            act[lo:hi] = a
         return act
+
+    def reset_rows(self, mask):
+        """A new game for the rows of ``mask`` (bool [batch]): what constructing a new ``Agent`` does."""
+        h0, h1, a = self.state
+        m = mask.to(h0.device).unsqueeze(1)
+        h0.masked_fill_(m, 0), h1.masked_fill_(m, 0), a.masked_fill_(m, 0)
+        a[:, 0] = torch.where(m.view(-1), torch.ones_like(a[:, 0]), a[:, 0])
+        self.calls.masked_fill_(m.view(-1), 0)
 
     def update(self, actions, imitate):
         return None

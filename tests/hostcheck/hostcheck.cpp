@@ -20,6 +20,7 @@ struct HcHandle {
     SfTabs t;
     std::vector<void *> allocs;
     unsigned long long stats[SF_STAT_COUNT];
+    uint16_t bt[SF_BT_ENTRIES]; /* the bullet-flag table of whichever arena is being stepped */
     template <class T> T *alloc(size_t n)
     {
         void *p = calloc(n, sizeof(T));
@@ -72,6 +73,7 @@ HcHandle *hc_create(const sf_config *cfg)
     d.pow_lut = h->tabs.pow_lut.data(), d.pow_lut_len = (int32_t)h->tabs.pow_lut.size();
     h->t.smap = d.smap, h->t.exp_tab = d.exp_tab, h->t.log_tab = d.log_tab;
     h->t.rng_cst = d.rng_cst, h->t.E = d.E;
+    h->t.bt = h->bt, h->t.bt_stride = 1;
     for (int env = 0; env < d.n_envs; ++env) {
         int64_t ge = k.env_id_base + env;
         sf_reset_body(d, k, h->t, env, sf_synth_tb(ge), sf_synth_serial(ge, 0), 0);
@@ -151,6 +153,12 @@ int hc_observe(HcHandle *h, int env, int slot, float *out, int raw)
     return SF_OBS_LEN;
 }
 
+#ifdef SF_DEBUG_HIST
+void hc_dbg_hist(unsigned long long *out)
+{
+    for (int i = 0; i < 256; ++i) out[i] = sf_dbg_hist[i];
+}
+#endif
 int hc_n_agents(HcHandle *h) { return h->k.n_agents; }
 int hc_compute_damage(int x, int y) { return sfhost::compute_damage(x, y); }
 float hc_obs_transform_milli(int n) { return sfhost::obs_transform_milli(n); }

@@ -13,7 +13,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 from strikeforce_b200 import config as sfcfg  # noqa: E402
 
-LIB_PATH = os.path.join(HERE, "libhostcheck.so")
+# HOSTCHECK_CFLAGS builds a variant next to the default one (e.g. "-DSF_BF_WORDS=1": a bullet-flag
+# filter so small that nearly every look-up takes the confirming walk over the bullets)
+EXTRA = os.environ.get("HOSTCHECK_CFLAGS", "").split()
+LIB_PATH = os.path.join(HERE, "libhostcheck%s.so" % ("_" + "".join(c for c in "".join(EXTRA) if c.isalnum()) if EXTRA else ""))
 _lib = None
 
 
@@ -26,7 +29,7 @@ def build(force=False):
         return
     subprocess.check_call([
         "g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
-        "-I" + os.path.join(ROOT, "strikeforce_b200", "csrc"), "-x", "c++", srcs[0], "-o", LIB_PATH])
+        "-I" + os.path.join(ROOT, "strikeforce_b200", "csrc")] + EXTRA + ["-x", "c++", srcs[0], "-o", LIB_PATH])
 
 
 def lib():

@@ -369,6 +369,9 @@ def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):
                     self.agent = self.p1 if phase == sfcfg.OBS_P1 else self.p2
                     return super().bot(s, agent_mask, phase)
 
+                def agents(self):
+                    return [self.p1, self.p2]
+
             c = TwoAgents()
             c.agent = c.p1
             stats = bots.play(sim, c, 12)

@@ -203,6 +203,58 @@ def _hosted_match_with_reference_clients(arena_data, table, T):
         host.close(), listener.close()
 
 
+def test_a_silent_client_is_a_gone_client(arena_data):
+    """server.cpp:265-279 gives every match socket a 500 ms receive time-out and my_recv plays '_'
+    for a socket that fails: a stalled player must not freeze the match (nor the lobby)."""
+    import time
+    teams, tb, serial = [1, 2, 1], 1700000123, 99
+    sheets = {i: "p%d\n" % i + "\n".join(str(int(v)) for v in arena_data.player_sheet("account1")) for i in range(3)}
+    listener = socket.socket()
+    listener.bind(("127.0.0.1", 0))
+    listener.listen(8)
+    port = listener.getsockname()[1]
+    host = ms.MatchHost(teams, "pw", tb, serial, local_seats={1: sheets[1]}, tick_timeout=0.2, lobby_timeout=0.3)
+    lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
+    lobby.start()
+    mute = socket.create_connection(("127.0.0.1", port))  # connects and never says a word
+    script0 = [(ord("+"), set())] * 3 + [(ord("w"), set())] * 3
+    c0 = ScriptedClient(port, b"pw", sheets[0], script0)
+    c0.start()
+    wait_for_seat(host, 0)
+
+    class Staller(ScriptedClient):  # plays two ticks, then keeps the connection open and goes quiet
+        def run(self):
+            s = socket.create_connection(("127.0.0.1", self.port))
+            ms.send_cstr(s, self.password)
+            assert ms.recv_cstr(s) == b"A"
+            ms.recv_cstr(s), ms.recv_cstr(s)
+            ms.send_cstr(s, self.sheet_text.encode())
+            for _ in range(4):
+                ms.recv_cstr(s)
+            for _ in range(2):
+                s.sendall(b"+\0")
+                ms.recv_cstr(s), ms.recv_cstr(s)
+            time.sleep(3.0)
+            s.close()
+
+    c2 = Staller(port, b"pw", sheets[2], [])
+    c2.start()
+    lobby.join(10)
+    assert not lobby.is_alive() and sorted(host.socks) == [0, 2], "the mute connection must not hold a seat"
+    mute.close()
+    host.handshake()
+    rows = []
+    t0 = time.time()
+    winner, ticks = ms.host_match(host, rows.append, lambda seat: ord("+"), max_ticks=6)
+    assert time.time() - t0 < 2.5, "a stalled client froze the match"
+    c0.join(10)
+    assert c0.error is None, c0.error
+    # tick 2: seat 2 is silent -> '_' for everybody, announced once, gone afterwards
+    assert rows[2][2] == ord("_") and rows[3][2] == ord("+") and not host.alive[2]
+    assert c0.received[2] == bytes([ord("+"), ord("_")]) and c0.received[3] == bytes([ord("+")])
+    host.close()
+
+
 def test_reference_clients_join_a_hosted_match(arena_data):
     """PINS the protocol side: two processes run the UNMODIFIED reference client (its own network code,
     gameplay.hpp:66-193, through oracle/ref_harness) against MatchHost; every tick the state of each

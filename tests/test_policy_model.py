@@ -83,7 +83,7 @@ def test_batched_forward_matches_the_reference_network():
 
 def test_policy_agent_is_seeded_and_batched():
     m = formula_model()
-    a1, a2 = PolicyAgent(m, 4, device="cpu", seed=3), PolicyAgent(m, 4, device="cpu", seed=3)
+    a1, a2 = PolicyAgent(m, 4, device="cpu", seed=3, t_initial=0), PolicyAgent(m, 4, device="cpu", seed=3, t_initial=0)
     x = torch.cat([formula_obs(s) for s in range(4)])
     for _ in range(3):
         r1, r2 = a1.predict(x), a2.predict(x)
@@ -98,10 +98,39 @@ def test_chunked_predict_is_the_same_policy():
     from strikeforce_b200 import policy
     torch.manual_seed(0)
     m = policy.AgentModel()
-    a = policy.PolicyAgent(m, 10, device="cpu", seed=5)
-    b = policy.PolicyAgent(m, 10, device="cpu", seed=5, chunk=4)
+    a = policy.PolicyAgent(m, 10, device="cpu", seed=5, t_initial=1)
+    b = policy.PolicyAgent(m, 10, device="cpu", seed=5, chunk=4, t_initial=1)
     x = torch.rand(10, 32, 31, 31)
     for _ in range(3):
         assert a.predict(x).tolist() == b.predict(x).tolist()
         for s, t in zip(a.state, b.state):
             assert torch.allclose(s, t, atol=1e-6)
+
+
+def test_policy_agent_follows_the_reference_agent_around_the_network():
+    """Agent::predict (bots/bot-0.5/Agent.hpp:178-215): action 0 for the first T_initial calls without
+    touching the network's memory; without SLOWMOTION action 0 is drawn half of the time; a new
+    game (reset_rows) starts both over for the rows it names."""
+    torch.manual_seed(1)
+    m = formula_model()
+    x = torch.cat([formula_obs(s) for s in range(6)])
+    a = PolicyAgent(m, 6, device="cpu", seed=7)
+    s0 = [t.clone() for t in a.state]
+    for _ in range(10):  # T_initial = 10 (Agent.hpp:274)
+        assert a.predict(x).tolist() == [0] * 6
+        assert all(torch.equal(u, v) for u, v in zip(a.state, s0)), "the warm-up must not run the recurrent network"
+    acts = torch.stack([a.predict(x) for _ in range(12)])
+    assert int(acts.max()) > 0 and not all(torch.equal(u, v) for u, v in zip(a.state, s0))
+    # a new game for rows 1 and 4 only
+    before = [t.clone() for t in a.state]
+    mask = torch.tensor([False, True, False, False, True, False])
+    a.reset_rows(mask)
+    for t, b0, z in zip(a.state, before, s0):
+        assert torch.equal(t[mask], z[mask]) and torch.equal(t[~mask], b0[~mask])
+    nxt = a.predict(x)
+    assert nxt[mask].tolist() == [0, 0] and a.calls.tolist() == [10, 1, 10, 10, 1, 10]
+    # the build without SLOWMOTION: P(action 0) = 0.5 whatever the network says
+    b = PolicyAgent(m, 6, device="cpu", seed=11, t_initial=0, slowmotion=False)
+    draws = torch.stack([b.predict(x) for _ in range(400)])
+    frac0 = float((draws == 0).float().mean())
+    assert 0.44 < frac0 < 0.56, frac0

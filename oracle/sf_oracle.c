@@ -1360,3 +1360,36 @@ long sfo_run_stream(sfo_arena *a, int64_t env, int level, const char *table, int
     if (hash_out) *hash_out = sfo_hash(a) + acc;
     return n_steps;
 }
+
+/* The same free-running workload, but with a CHECKSUM OF THE WHOLE TRAJECTORY: after every step
+ * (and any auto-reset it triggers) the canonical-state hash is folded into
+ * chk = mix64(chk ^ hash).  Optionally the observation of human slot 0 after the last step.
+ * This is what the full-size GPU parity tests compare against (one value per arena covers every
+ * step of it).  Returns the number of episodes that ended. */
+long sfo_run_trace(sfo_arena *a, int64_t env, int level, const char *table, int table_len, long n_steps,
+                   uint64_t *chk_out, uint64_t *last_hash_out, float *obs_out)
+{
+    int64_t episode = 0;
+    uint64_t streams[SF_MAX_PLAYERS];
+    for (int ag = 0; ag < SF_MAX_PLAYERS; ++ag) streams[ag] = sf_synth_stream_init(env, ag);
+    int n_agents = a->mode == SF_MODE_ROYALE ? a->n_players : (a->mode == SF_MODE_SQUAD && a->squad_agents) ? 10 : 1;
+    sfo_reset(a, level, sf_synth_tb(env), sf_synth_serial(env, episode));
+    uint8_t act[SF_MAX_PLAYERS];
+    uint64_t chk = 0, h = sfo_hash(a);
+    for (long s = 0; s < n_steps; ++s) {
+        for (int ag = 0; ag < SF_MAX_PLAYERS; ++ag) {
+            uint64_t z = sf_synth_stream_next(&streams[ag]);
+            act[ag] = (uint8_t)table[z % (uint64_t)table_len];
+        }
+        if (sfo_step(a, act, n_agents) != SF_RUNNING) {
+            ++episode;
+            sfo_reset(a, level, sf_synth_tb(env), sf_synth_serial(env, episode));
+        }
+        h = sfo_hash(a);
+        chk = sf_mix64(chk ^ h);
+    }
+    if (chk_out) *chk_out = chk;
+    if (last_hash_out) *last_hash_out = h;
+    if (obs_out && sfo_observe(a, 0, obs_out) != SF_OBS_LEN) obs_out[0] = -1.0f; /* no active agent: the reference builds nothing */
+    return (long)episode;
+}

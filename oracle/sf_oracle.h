@@ -5,7 +5,7 @@
  * functions of gameplay.hpp, the entity rules of Character.hpp / Item.hpp and the
  * observation builder of bots/bot-0.5/Custom.hpp.  Every function in sf_oracle.c cites the
  * reference file:line it follows.  It is pinned against the UNMODIFIED reference compiled
- * into oracle/_ref/libsfref.so (oracle/ref_harness) by tests/test_oracle_vs_reference.py
+ * into oracle/_ref/libsfref.so (oracle/ref_harness) by tests/test_oracle_golden.py
  * and against the golden vectors under tests/golden/.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
@@ -65,6 +65,12 @@ float sfo_obs_transform(float x);
 /* free-running synthetic workload (sf_synth.h) with auto-reset; returns env-steps executed */
 long sfo_run_stream(sfo_arena *a, int64_t env, int level, const char *table, int table_len,
                     long n_steps, int with_obs, uint64_t *hash_out);
+
+/* the same workload with a checksum over the canonical-state hash after EVERY step
+   (chk = mix64(chk ^ hash)), the last hash and optionally slot 0's observation at the end;
+   returns the number of episodes that ended */
+long sfo_run_trace(sfo_arena *a, int64_t env, int level, const char *table, int table_len, long n_steps,
+                   uint64_t *chk_out, uint64_t *last_hash_out, float *obs_out);
 
 #ifdef __cplusplus
 }

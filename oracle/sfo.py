@@ -57,6 +57,9 @@ def lib():
         L.sfo_run_stream.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_char_p, C.c_int, C.c_long, C.c_int,
                                      C.POINTER(C.c_uint64)]
         L.sfo_run_stream.restype = C.c_long
+        L.sfo_run_trace.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_char_p, C.c_int, C.c_long,
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+        L.sfo_run_trace.restype = C.c_long
         _lib = L
     return _lib
 
@@ -154,6 +157,15 @@ class Arena:
         h = C.c_uint64(0)
         n = lib().sfo_run_stream(self._h, env, level, bytes(table), len(table), n_steps, int(with_obs), C.byref(h))
         return n, int(h.value)
+
+    def run_trace(self, env, level, n_steps, table, with_obs=False):
+        """(episodes ended, checksum over the state hash after every step, last hash, observation of
+        slot 0 after the last step or None): the synthetic workload of include/sf_synth.h with auto-reset."""
+        chk, last = C.c_uint64(0), C.c_uint64(0)
+        obs = np.empty(OBS_LEN, dtype=np.float32) if with_obs else None
+        n = lib().sfo_run_trace(self._h, env, level, bytes(table), len(table), n_steps, C.byref(chk), C.byref(last),
+                                obs.ctypes.data if with_obs else None)
+        return n, int(chk.value), int(last.value), obs
 
 
 def parse_record(rec):

@@ -233,8 +233,12 @@ SF_FN uint32_t sf_rng_log(const SfEnv &e, int i) { return (e.Lp[i >> 1] >> (16 *
  * the 16-bit complement of the entry. */
 SF_FN uint32_t sf_exp_m1(const SfTabs &t, uint32_t k2)
 {
+#ifdef SF_FULL_EXP /* A/B build: the whole table in shared memory (a 228 KB carve-out, 28 KB of L1) */
+    return *(const uint16_t *)((const uint8_t *)t.exp_tab + k2);
+#else
     const uint32_t v = *(const uint16_t *)((const uint8_t *)t.exp_tab + (k2 & 0xFFFEu));
     return (k2 & 0x10000u) ? (v ^ 0xFFFFu) : v;
+#endif
 }
 
 SF_FN uint32_t sf_rng_term(const SfTabs &t, uint32_t L, uint32_t c)

@@ -25,7 +25,11 @@
 #ifndef SF_CTA
 #define SF_CTA 896 /* threads per CTA = arenas in flight per SM (one CTA per SM); 28 warps x 148 SMs = 4144 >= the 4096 chunks of 131072 arenas, 72 registers per thread */
 #endif
+#ifdef SF_FULL_EXP
+#define SF_SMEM_EXP 131072
+#else
 #define SF_SMEM_EXP 65536 /* the first half of the exp table (sf_exp_m1) */
+#endif
 #define SF_SMEM_MAP SF_TCELLS /* 9,984, a multiple of 16 */
 #define SF_SMEM_BT (SF_CTA * SF_BT_ENTRIES * 2) /* the bullet-flag tables of the CTA's arenas, [entry][thread] */
 #define SF_SMEM_BYTES (SF_SMEM_EXP + SF_SMEM_MAP + SF_SMEM_BT) /* 161,536 B: the 164 KB carve-out, 92 KB of L1 */
@@ -83,27 +87,34 @@ __device__ __forceinline__ void sf_flush_stats(const SfDev &d, const SfStatDelta
 #undef SF_RED_S
 }
 
-/* one env-step (HALF: both halves, A only, B only) for every arena of the handle */
+/* one env-step (HALF: both halves, A only, B only) for every arena of the handle.
+ *
+ * lpw = arenas per warp (a power of two).  A full batch puts 32 arenas into every warp: one wave of
+ * 131,072 arenas is what the machine holds.  A step of ONE warp lasts ~0.8 ms however few warps there
+ * are (the tick is a serial chain, and the 32 arenas of a warp execute the union of their
+ * branches), so a batch that would leave warp slots empty is spread over more warps with fewer
+ * arenas each (sf_launch_step picks lpw): the extra lanes idle, the chain of every warp gets
+ * shorter because fewer arenas diverge in it. */
 template <int HALF>
 __global__ void __launch_bounds__(SF_CTA, 1)
-sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *__restrict__ actions)
+sf_step_kernel(const SfDev d, const __grid_constant__ SfConst k, const uint8_t *__restrict__ actions, int lpw)
 {
     SfTabs t;
     sf_stage_tables(d, t);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = d.E >> 5;
+    const int nchunks = (d.n_envs + lpw - 1) / lpw;
 #ifndef SF_NO_PHASE_BARRIERS
     /* every warp of the CTA makes the same number of passes (a pass without a chunk walks through
        with all lanes off), so that the phase barriers of sf_step_halves line up */
     const int per_pass = gridDim.x * (SF_CTA / 32);
     for (int base = 0; base < nchunks; base += per_pass) {
         const int chunk = base + blockIdx.x + gridDim.x * warp;
-        int env = chunk < nchunks ? chunk * 32 + lane : lane;
-        bool valid = chunk < nchunks && env < d.n_envs;
+        bool valid = chunk < nchunks && lane < lpw && chunk * lpw + lane < d.n_envs;
+        int env = valid ? chunk * lpw + lane : lane; /* an idle lane reads some arena's header and writes nothing */
 #else
     for (int chunk = blockIdx.x + gridDim.x * warp; chunk < nchunks; chunk += gridDim.x * (SF_CTA / 32)) {
-        int env = chunk * 32 + lane;
-        bool valid = env < d.n_envs;
+        bool valid = lane < lpw && chunk * lpw + lane < d.n_envs;
+        int env = valid ? chunk * lpw + lane : lane;
 #endif
         SfStatDelta sd;
         memset(&sd, 0, sizeof sd);
@@ -194,83 +205,94 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
 /* gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158).
  *
  * The product is 123,008 contiguous bytes per (arena, observer), almost all zeros (floor, cells
- * outside the map) -- a pure HBM-write problem whose enemy is latency: every dependent load in
- * front of a store is time in which the CTA writes nothing.  Persistent CTAs (four per SM) build
- * each observation in shared memory a few channels at a time and hand the tiles to the TMA engine
- * with cp.async.bulk (shared -> global, bulk-group completion), so the stores are whole aligned
- * lines:
+ * outside the map) -- a pure HBM-write problem whose enemy is latency: a CTA that waits (for a
+ * load, for a barrier, for a store engine to release a buffer) writes nothing, and the bytes it
+ * has in flight are all the bandwidth it gets.  So the kernel keeps nothing of the OUTPUT in
+ * shared memory: it builds a small description of the window and then streams the 7,688 16-byte
+ * chunks of the observation straight from registers with plain coalesced stores (512 contiguous
+ * bytes per warp instruction; a store holds no resource of the CTA once it has issued, and 25 KB
+ * of shared memory per CTA leave room for 7 CTAs per SM).
  *   1. entity -> window maps for the owning bullets and player-built cells (shared memory);
- *   2. the window is classified in one pass into STATIC cells (walls, stairs, exits with nothing on
- *      them: their features follow from the map byte, which rides in the list entry) and DYNAMIC
- *      cells (anything in the overlay, or a bullet flag); floor and cells outside the map are
- *      neither, and stay zero;
- *   3. describe() runs ONCE per dynamic cell -- all its entity loads in one round -- and the 32
- *      transformed features go to a channel-major cache in shared memory;
- *   4. per tile: wait until the TMA has read what the tile buffer held two tiles ago (the buffers
- *      alternate, so the store of tile k drains while tile k+1 is written), copy the static
- *      constants and the cached features of the listed cells into it (the first tiles of a window
- *      first wipe the cells the window before it listed; everything else in a tile is zero and
- *      stays zero), fence to the async proxy, one thread issues the bulk store. */
+ *   2. the window is classified into a CODE per cell: 0 = nothing to show (floor, outside the map),
+ *      1..15 = the static flags of a cell with nothing on it (wall, stairs, exit), 16 + i = the
+ *      i-th DYNAMIC cell (anything in the overlay, or a bullet flag);
+ *   3. describe() runs ONCE per dynamic cell -- all its entity loads in one round -- and its 32
+ *      transformed features become row 16 + i of a table whose rows 1..15 hold what describe()
+ *      gives for the static flags alone (filled once per CTA);
+ *   4. the copy-out: 961 = 1 (mod 4), so every four channels are exactly 961 chunks and chunk q
+ *      covers the same (channel offset, cell) quadruple in each of the eight 4-channel groups; a
+ *      thread reads the four codes of its chunk once and then writes the chunk of every group:
+ *      four predicated table reads and one 16-byte store each. */
 #ifndef SF_OBS_CTA
 #define SF_OBS_CTA 128
 #endif
 #ifndef SF_OBS_CTAS_PER_SM
-#define SF_OBS_CTAS_PER_SM 4
-#endif
-#ifndef SF_OBS_TILE_CH
-#define SF_OBS_TILE_CH 4 /* channels per shared-memory tile */
-#endif
-#ifndef SF_OBS_NBUF
-#define SF_OBS_NBUF 2    /* tile buffers per CTA */
+#define SF_OBS_CTAS_PER_SM 7
 #endif
 #ifndef SF_OBS_CACHE
-#define SF_OBS_CACHE 128 /* dynamic cells whose features are cached (the rest are described again per tile) */
+#define SF_OBS_CACHE 144 /* dynamic cells with a table row; any beyond are described again during the copy-out */
 #endif
-#define SF_OBS_TILE_FLOATS (SF_OBS_TILE_CH * SF_OBS_CELLS) /* 4 x 961 floats = 15,376 B, a multiple of 16 */
-#define SF_OBS_PARTS (SF_OBS_CH / SF_OBS_TILE_CH)
-#define SF_OBS_LIST 992 /* uint16 entries per cell list (>= 961, keeps the arrays 16-byte aligned) */
-#define SF_OBS_SMEM (SF_OBS_NBUF * SF_OBS_TILE_FLOATS * 4 + SF_OBS_CACHE * SF_OBS_CH * 4 + 4 * SF_OBS_LIST * 2 + 16)
-static_assert(SF_OBS_CH % SF_OBS_TILE_CH == 0 && (SF_OBS_TILE_FLOATS * 4) % 16 == 0, "bulk copies move multiples of 16 bytes");
+#define SF_OBS_ROWS (16 + SF_OBS_CACHE)
+#define SF_OBS_PITCH (SF_OBS_CH + 1) /* floats per table row: odd, so that rows fall into different banks */
+#define SF_OBS_LIST 976              /* entries per per-cell array (>= 961, keeps the arrays 16-byte aligned) */
+#define SF_OBS_BEYOND 0xFFFFu        /* code of a dynamic cell without a table row */
+#define SF_OBS_GROUP (SF_OBS_CELLS)  /* chunks per 4-channel group: 4 * 961 floats / 4 */
+#define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + 16)
+static_assert(SF_OBS_CELLS % 4 == 1 && SF_OBS_CH % 4 == 0, "the copy-out relies on 4 channels = 961 whole chunks");
 
-__device__ __forceinline__ void sf_bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+__device__ __forceinline__ void sf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+/* (arena, observed human slot) of work item `item` */
+__device__ __forceinline__ void sf_obs_item(int item, int nsel, uint32_t agent_mask, int *env, int *slot)
 {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    uint32_t m = agent_mask;
+    for (int i = item % nsel; i > 0; --i) m &= m - 1;
+    *env = item / nsel, *slot = __ffs(m) - 1;
 }
-
-/* a list entry: window index (10 bits) | the low four bits of the static map byte << 10 */
-#define SF_OBS_W(entry) ((int)((entry) & 1023u))
-#define SF_OBS_ST(entry) ((uint32_t)(entry) >> 10)
-static_assert((M_WALL | M_UP | M_DOWN | M_EXIT) == 0xFu, "the static flags describe() reads ride in a list entry");
 
 __global__ void __launch_bounds__(SF_OBS_CTA, SF_OBS_CTAS_PER_SM)
 sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
                   int nsel, int n_items)
 {
-    float *tiles = reinterpret_cast<float *>(sf_smem);
-    float *cache = tiles + SF_OBS_NBUF * SF_OBS_TILE_FLOATS; /* [channel][cached cell] */
-    int16_t *bmap = reinterpret_cast<int16_t *>(cache + SF_OBS_CACHE * SF_OBS_CH);
+    float *feat = reinterpret_cast<float *>(sf_smem);                         /* [row][SF_OBS_PITCH] */
+    uint16_t *code = reinterpret_cast<uint16_t *>(feat + SF_OBS_ROWS * SF_OBS_PITCH); /* per window cell */
+    uint16_t *dlist = code + SF_OBS_LIST;                                     /* window index of dynamic cell i */
+    int16_t *bmap = reinterpret_cast<int16_t *>(dlist + SF_OBS_LIST);
     int16_t *tmap = bmap + SF_OBS_LIST;
-    /* this window's list and the last one's: static cells from the front, dynamic ones from the back */
-    uint16_t *list = reinterpret_cast<uint16_t *>(tmap + SF_OBS_LIST), *prev = list + SF_OBS_LIST;
-    int *count = reinterpret_cast<int *>(list + 2 * SF_OBS_LIST); /* [0] static, [1] dynamic */
+    int *count = reinterpret_cast<int *>(tmap + SF_OBS_LIST);
     SfTabs t;
     sf_global_tabs(d, t);
     uint32_t fb = 0;
-    const float lut_1000 = sf_obs_transform(d, 1000, &fb), lut_20 = sf_obs_transform(d, 20, &fb), lut_10 = sf_obs_transform(d, 10, &fb);
-    int ps_stat = 0, ps_dyn = 0; /* the last window's counts */
-    uint32_t tile_no = 0;        /* tiles stored so far by this CTA: buffer = tile_no % SF_OBS_NBUF */
-    /* the tiles are zero outside the listed cells at all times: they are cleared once, and a window
-       only wipes what the window before it wrote */
-    for (int i = threadIdx.x; i < SF_OBS_NBUF * SF_OBS_TILE_FLOATS / 4; i += SF_OBS_CTA)
-        reinterpret_cast<float4 *>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 16) { /* describe() of a cell with nothing on it depends on its static flags only (no memory access) */
+        SfEnv e0;
+        e0.mb[0] = e0.mb[1] = 0, e0.ntemp = 0, e0.level = 1, e0.hw_h = 0, e0.env = 0;
+        int32_t f[32];
+        sf_describe_cell(d, k, 0, e0, 0, threadIdx.x, 0u, 0u, -1, -1, f);
+#pragma unroll
+        for (int c = 0; c < SF_OBS_CH; ++c) feat[threadIdx.x * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
+    }
+    constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int env = item / nsel;
-        uint32_t m = agent_mask;
-        for (int i = item % nsel; i > 0; --i) m &= m - 1;
-        const int slot = __ffs(m) - 1;
+        int env, slot;
+        sf_obs_item(item, nsel, agent_mask, &env, &slot);
         float *out = obs + (size_t)item * SF_OBS_LEN;
+        /* The next window's header words are asked into L2 now and its cells when this window's
+           copy-out starts: by the time the CTA gets there they are a short trip away, and no
+           register has been held for them. */
+#ifdef SF_OBS_NO_PREFETCH /* A/B build */
+        const bool more = false;
+#else
+        const bool more = item + (int)gridDim.x < n_items;
+#endif
+        int env_n = 0, slot_n = 0;
+        if (more) {
+            sf_obs_item(item + gridDim.x, nsel, agent_mask, &env_n, &slot_n);
+            if (threadIdx.x == 0) {
+                sf_prefetch_l2(&d.misc[env_n]), sf_prefetch_l2(&d.mb[env_n]), sf_prefetch_l2(&d.mb[(size_t)d.E + env_n]);
+                sf_prefetch_l2(&d.ntemp[env_n]);
+                if (slot_n < k.cap_h) sf_prefetch_l2(&d.h_pw[(size_t)slot_n * d.E + env_n]), sf_prefetch_l2(&d.h_sel[(size_t)slot_n * d.E + env_n]);
+            }
+        }
         /* the few header words the features need */
         SfEnv e;
         const uint32_t misc = d.misc[env];
@@ -284,20 +306,20 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         int vf, vr, vc;
         sf_tcell_decode(vcell, &vf, &vr, &vc);
         const int r0 = vr - SF_OBS_R, c0 = vc - SF_OBS_R;
+        /* the loads of a thread's window cells are issued first: they are in flight while the entity
+           maps are filled */
+        uint32_t cv[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int w = threadIdx.x + q * SF_OBS_CTA;
+            const int cell = (observer && w < SF_OBS_CELLS) ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
+            cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
+        }
+        __syncthreads(); /* every thread is done with the last window's codes and table */
         for (int i = threadIdx.x; i < SF_OBS_CELLS; i += SF_OBS_CTA) bmap[i] = -1, tmap[i] = -1;
-        if (threadIdx.x < 2) count[threadIdx.x] = 0;
+        if (threadIdx.x == 0) *count = 0;
         __syncthreads();
         if (observer) {
-            /* the loads of a thread's eight window cells are issued first: they are in flight while
-               the entity maps are filled */
-            constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
-            uint32_t cv[PER];
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int w = threadIdx.x + q * SF_OBS_CTA;
-                const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
-                cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
-            }
             for (int b = threadIdx.x; b < SF_LIM_BULLETS; b += SF_OBS_CTA)
                 if (m2_test(e.mb, b) && (SF_AT(d.b_meta, b) & BF_OWNS)) {
                     int bf, br, bc;
@@ -313,100 +335,100 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                 if (tf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
                     tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
             }
-            __syncthreads();
-            /* a cell that carries nothing but a bullet flag has an empty overlay word: bmap lists it */
+        }
+        __syncthreads();
+        /* classification (a cell that carries nothing but a bullet flag has an empty overlay word:
+           bmap tells); one atomic per warp, not one per cell */
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int w = threadIdx.x + q * SF_OBS_CTA;
-                if (w < SF_OBS_CELLS) {
-                    const uint32_t entry = (uint32_t)w | ((cv[q] >> 16) & 0xFu) << 10;
-                    if ((cv[q] & 0xFFFFu) || bmap[w] >= 0) list[SF_OBS_LIST - 1 - atomicAdd(&count[1], 1)] = (uint16_t)entry;
-                    else if (entry >> 10) list[atomicAdd(&count[0], 1)] = (uint16_t)entry;
+        for (int q = 0; q < PER; ++q) {
+            const int w = threadIdx.x + q * SF_OBS_CTA;
+            const bool dyn = w < SF_OBS_CELLS && ((cv[q] & 0xFFFFu) || bmap[w] >= 0);
+            const unsigned md = __ballot_sync(0xffffffffu, dyn);
+            const unsigned lane = threadIdx.x & 31u;
+            int base = 0;
+            if (lane == 0 && md) base = atomicAdd(count, __popc(md));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (w < SF_OBS_CELLS) {
+                uint32_t cd = (cv[q] >> 16) & 0xFu; /* M_WALL | M_UP | M_DOWN | M_EXIT: rows 1..15 of the table */
+                if (dyn) {
+                    const int i = base + __popc(md & ((1u << lane) - 1u));
+                    cd = i < SF_OBS_CACHE ? 16u + (uint32_t)i : SF_OBS_BEYOND;
+                    if (i < SF_OBS_CACHE) dlist[i] = (uint16_t)w;
                 }
+                code[w] = (uint16_t)cd;
             }
         }
         __syncthreads();
-        const int n_stat = count[0], n_dyn = count[1];
-        /* describe() once per dynamic cell; its 32 transformed features wait in the cache */
-        for (int i = threadIdx.x; i < n_dyn && i < SF_OBS_CACHE; i += SF_OBS_CTA) {
-            const uint32_t entry = list[SF_OBS_LIST - 1 - i];
-            const int w = SF_OBS_W(entry), cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+        /* describe() once per dynamic cell; its 32 transformed features become a table row */
+        const int n_dyn = *count < SF_OBS_CACHE ? *count : SF_OBS_CACHE;
+        for (int i = threadIdx.x; i < n_dyn; i += SF_OBS_CTA) {
+            const int w = dlist[i], cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
             int32_t f[32];
             sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
 #pragma unroll
-            for (int c = 0; c < SF_OBS_CH; ++c) cache[c * SF_OBS_CACHE + i] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
+            for (int c = 0; c < SF_OBS_CH; ++c) feat[(16 + i) * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
         }
-#pragma unroll 1
-        for (int part = 0; part < SF_OBS_PARTS; ++part, ++tile_no) {
-            float *tile = tiles + (tile_no % SF_OBS_NBUF) * SF_OBS_TILE_FLOATS;
-#ifdef SF_OBS_TMA
-            /* the TMA must have read the buffer's previous content before it is overwritten; the
-               barrier also publishes the cache */
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SF_OBS_NBUF - 1) : "memory");
-            __syncthreads();
-#endif
-            if (part < SF_OBS_NBUF) { /* the buffer last held a tile of the window before: wipe its cells
-                                         (the barrier after it also publishes the cache) */
-                for (int i = threadIdx.x; i < ps_stat + ps_dyn; i += SF_OBS_CTA) {
-                    const int w = SF_OBS_W(prev[i < ps_stat ? i : SF_OBS_LIST - 1 - (i - ps_stat)]);
+        if (more) { /* the next window: its cells, the bullet and built-cell rows of its arena */
+            const uint32_t misc_n = d.misc[env_n]; /* in L2 by now */
+            if (slot_n < (int)((misc_n >> 16) & 0xFFu)) {
+                const int vcell_n = (int)(d.h_pw[(size_t)slot_n * d.E + env_n] & POS_CELL);
 #pragma unroll
-                    for (int c = 0; c < SF_OBS_TILE_CH; ++c) tile[c * SF_OBS_CELLS + w] = 0.f;
+                for (int q = 0; q < PER; ++q) { /* one request per 64-byte overlay granule would do; neighbours merge */
+                    const int w = threadIdx.x + q * SF_OBS_CTA;
+                    const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell_n, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
+                    if (cell >= 0 && ((cell & 31) == 0 || w % SF_OBS_WIN == 0 || (cell & 7) == 0))
+                        sf_prefetch_l2(&d.grid[(size_t)env_n * SF_GRID_STRIDE + (size_t)cell]);
                 }
-                __syncthreads();
-            }
-            for (int i = threadIdx.x; i < n_stat; i += SF_OBS_CTA) {
-                const uint32_t entry = list[i];
-                const int w = SF_OBS_W(entry);
-                int32_t f[32];
-                sf_describe_cell(d, k, env, e, 0, SF_OBS_ST(entry), 0u, team, -1, -1, f); /* no memory access */
-                for (int c = 0; c < SF_OBS_TILE_CH; ++c) { /* a static cell's features are 1, 0.02 or 0.01 */
-                    const int32_t v = f[part * SF_OBS_TILE_CH + c];
-                    tile[c * SF_OBS_CELLS + w] = v == 0 ? 0.f : v == 1000 ? lut_1000 : v == 20 ? lut_20 : v == 10 ? lut_10
-                                                                                          : sf_obs_transform(d, v, &fb);
+                if (threadIdx.x < SF_LIM_BULLETS && threadIdx.x < (unsigned)k.cap_b) {
+                    sf_prefetch_l2(&d.b_meta[(size_t)threadIdx.x * d.E + env_n]);
+                    sf_prefetch_l2(&d.b_pw[(size_t)threadIdx.x * d.E + env_n]);
                 }
+                if (threadIdx.x < 8) sf_prefetch_l2(&d.t_cell[(size_t)env_n * d.cap_t + threadIdx.x * 32]);
             }
-            for (int i = threadIdx.x; i < n_dyn; i += SF_OBS_CTA) {
-                const uint32_t entry = list[SF_OBS_LIST - 1 - i];
-                const int w = SF_OBS_W(entry);
-                if (i < SF_OBS_CACHE) {
+        }
+        __syncthreads();
+        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM */
+        float4 *dst = reinterpret_cast<float4 *>(out);
+        for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
+            int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
+            int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
+            bool beyond = false;
 #pragma unroll
-                    for (int c = 0; c < SF_OBS_TILE_CH; ++c)
-                        tile[c * SF_OBS_CELLS + w] = cache[(part * SF_OBS_TILE_CH + c) * SF_OBS_CACHE + i];
-                } else { /* more dynamic cells than the cache holds: described again for every tile */
-                    const int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
-                    int32_t f[32];
-                    sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
-                    for (int c = 0; c < SF_OBS_TILE_CH; ++c) {
-                        const int32_t v = f[part * SF_OBS_TILE_CH + c];
-                        tile[c * SF_OBS_CELLS + w] = v ? sf_obs_transform(d, v, &fb) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t cd = code[w];
+                row[j] = cd ? (int)cd * SF_OBS_PITCH + cc : -1;
+                if (cd == SF_OBS_BEYOND) beyond = true, row[j] = -2 - w;
+                if (++w == SF_OBS_CELLS) w = 0, ++cc;
+            }
+            if (!beyond) {
+#pragma unroll
+                for (int g = 0; g < SF_OBS_CH / 4; ++g) {
+                    float4 v;
+                    v.x = row[0] >= 0 ? feat[row[0] + 4 * g] : 0.f;
+                    v.y = row[1] >= 0 ? feat[row[1] + 4 * g] : 0.f;
+                    v.z = row[2] >= 0 ? feat[row[2] + 4 * g] : 0.f;
+                    v.w = row[3] >= 0 ? feat[row[3] + 4 * g] : 0.f;
+                    __stcs(dst + g * SF_OBS_GROUP + q, v);
+                }
+            } else { /* more dynamic cells than table rows (rare): those are described here, once per chunk */
+                float val[4][SF_OBS_CH / 4];
+                int cj = (4 * q) / SF_OBS_CELLS, wj = 4 * q - cj * SF_OBS_CELLS;
+                for (int j = 0; j < 4; ++j) {
+                    if (row[j] <= -2) {
+                        const int cell = sf_obs_cell(vcell, wj / SF_OBS_WIN, wj % SF_OBS_WIN);
+                        int32_t f[32];
+                        sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[wj], tmap[wj], f);
+                        for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = f[4 * g + cj] ? sf_obs_transform(d, f[4 * g + cj], &fb) : 0.f;
+                    } else {
+                        for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = row[j] >= 0 ? feat[row[j] + 4 * g] : 0.f;
                     }
+                    if (++wj == SF_OBS_CELLS) wj = 0, ++cj;
                 }
+                for (int g = 0; g < SF_OBS_CH / 4; ++g)
+                    __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
             }
-#ifdef SF_OBS_TMA
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> async proxy */
-            __syncthreads();
-            if (threadIdx.x == 0) sf_bulk_store(out + part * SF_OBS_TILE_FLOATS, tile, SF_OBS_TILE_FLOATS * 4);
-#else
-            /* copy-out: whole 512-byte runs per warp, fire and forget -- a store holds no shared
-               memory once it has issued, so the bytes in flight are not bounded by the tile buffers.
-               One barrier per tile is enough: a thread that starts filling this buffer again (two
-               tiles on) has passed the barrier of the tile in between, which every thread reaches
-               only after its part of this copy-out. */
-            __syncthreads();
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(tile);
-                float4 *dst = reinterpret_cast<float4 *>(out + part * SF_OBS_TILE_FLOATS);
-#pragma unroll 4
-                for (int i = threadIdx.x; i < SF_OBS_TILE_FLOATS / 4; i += SF_OBS_CTA) __stcs(dst + i, src[i]);
-            }
-#endif
         }
-        uint16_t *sw = list;
-        list = prev, prev = sw, ps_stat = n_stat, ps_dyn = n_dyn;
     }
-#ifdef SF_OBS_TMA
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }
 
@@ -450,6 +472,7 @@ struct sf_handle {
     int64_t *d_tb = nullptr, *d_serial = nullptr;
     int device = 0, n_sm = 0;
     bool between_halves = false; /* sf_step_a has run, sf_step_b has not: the P2 observation point */
+    int lanes_per_warp = 0;      /* 0 = chosen from the batch size; SF_LANES_PER_WARP overrides (measurements) */
     long long launches = 0;
     std::string err;
 };
@@ -580,6 +603,10 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     h->d.n_envs = cfg->n_envs;
     h->d.E = (cfg->n_envs + 31) / 32 * 32;
     h->d.cap_t = (h->k.cap_t + 7) / 8 * 8;
+    if (const char *v = getenv("SF_LANES_PER_WARP")) {
+        const int n = atoi(v);
+        if (n == 1 || n == 2 || n == 4 || n == 8 || n == 16 || n == 32) h->lanes_per_warp = n;
+    }
     cudaError_t ce = cudaGetDevice(&h->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
     int smem_optin = 0;
@@ -691,11 +718,18 @@ static int sf_launch_step(sf_handle *h, int half, const uint8_t *d_actions, cuda
         return sf_fail(h, SF_ERR_ARG, half == SF_HALF_B ? "sf_step_b: no sf_step_a before it"
                                                         : "sf_step / sf_step_a: the step opened by sf_step_a is still waiting for sf_step_b");
     h->between_halves = half == SF_HALF_A;
-    int nchunks = h->d.E / 32;
-    int grid = nchunks < h->n_sm ? nchunks : h->n_sm; /* one persistent CTA per SM; warps take chunks round-robin */
-    if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
-    else if (half == SF_HALF_A) sf_step_kernel<SF_HALF_A><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, nullptr);
-    else sf_step_kernel<SF_HALF_B><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions);
+    /* arenas per warp: as few as still fit the batch into one wave of warps (see sf_step_kernel) */
+    const int slots = h->n_sm * (SF_CTA / 32);
+    int lpw = h->lanes_per_warp;
+    if (lpw <= 0) {
+        lpw = 1;
+        while (lpw < 32 && (h->d.n_envs + lpw - 1) / lpw > slots) lpw *= 2;
+    }
+    const int nchunks = (h->d.n_envs + lpw - 1) / lpw;
+    int grid = nchunks < h->n_sm ? nchunks : h->n_sm; /* one persistent CTA per SM; warps take chunks round-robin over the CTAs */
+    if (half == SF_HALF_BOTH) sf_step_kernel<SF_HALF_BOTH><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions, lpw);
+    else if (half == SF_HALF_A) sf_step_kernel<SF_HALF_A><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, nullptr, lpw);
+    else sf_step_kernel<SF_HALF_B><<<grid, SF_CTA, SF_SMEM_BYTES, s>>>(h->d, h->k, d_actions, lpw);
     h->launches += 1;
     SF_CUDA(h, cudaGetLastError());
     return SF_OK;

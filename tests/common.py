@@ -79,3 +79,68 @@ def record_crcs(rec):
             kept.append(rec[i:i + n])
         i += n
     return zlib.crc32(rec.tobytes()), zlib.crc32(np.concatenate(kept).tobytes())
+
+
+# ------------------------------------------------------------------ whole-trajectory checks
+
+MASK64 = (1 << 64) - 1
+
+
+def mix64(x):
+    """include/sf_canon.h sf_mix64 on a Python int"""
+    x &= MASK64
+    x ^= x >> 30
+    x = (x * 0xbf58476d1ce4e5b9) & MASK64
+    x ^= x >> 27
+    x = (x * 0x94d049bb133111eb) & MASK64
+    return x ^ (x >> 31)
+
+
+def torch_mix64(torch, x):
+    """sf_mix64 on an int64 tensor holding uint64 bit patterns (multiplication wraps; the shifts are made logical)"""
+    def lshr(v, s):
+        return (v >> s) & ((1 << (64 - s)) - 1)
+
+    def i64(c):
+        return c - (1 << 64) if c >= (1 << 63) else c
+    x = x ^ lshr(x, 30)
+    x = x * i64(0xbf58476d1ce4e5b9)
+    x = x ^ lshr(x, 27)
+    x = x * i64(0x94d049bb133111eb)
+    return x ^ lshr(x, 31)
+
+
+def _trace_worker(job):
+    """One process of oracle_traces: plays the synthetic workload (include/sf_synth.h, auto-reset)
+    for its arenas inside the C oracle and returns, per arena, (episodes, checksum over the state hash
+    after every step, last hash, observation of slot 0 at the end as uint32 words or None)."""
+    kw, envs, steps, table, with_obs = job
+    import sfo as _sfo
+    from strikeforce_b200 import data as _data
+    arena = _data.load_default()
+    span = kw["level_max"] - kw["level_min"] + 1
+    out = []
+    arenas = {}
+    for e in envs:
+        lvl = kw["level_min"] + e % span
+        if lvl not in arenas:
+            c = sfcfg.make_config(arena, mode=kw["mode"], level_min=lvl, squad_agents=kw.get("squad_agents", False),
+                                  max_steps=kw.get("max_steps", 0), player=kw.get("player", "account1"),
+                                  teams=kw.get("teams"), caps=kw.get("caps"))
+            arenas[lvl] = _sfo.Arena(c)
+        n, chk, last, obs = arenas[lvl].run_trace(e, lvl, steps, table, with_obs)
+        out.append((e, n, chk, last, None if obs is None else obs.view(np.uint32).copy()))
+    return out
+
+
+def oracle_traces(kw, envs, steps, table, with_obs=False, procs=None):
+    """{env: (episodes, trajectory checksum, last hash, obs words)} from the C oracle, all host cores."""
+    import multiprocessing as mp
+    import os
+    envs = list(envs)
+    procs = procs or min(len(envs), os.cpu_count() or 1)
+    jobs = [(kw, envs[i::procs], steps, bytes(table), with_obs) for i in range(procs)]
+    ctx = mp.get_context("spawn")  # the parent may hold a CUDA context: never fork it
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_trace_worker, jobs)
+    return {r[0]: r[1:] for part in res for r in part}

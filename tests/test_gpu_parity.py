@@ -296,28 +296,78 @@ def _sampled_parity(torch, arena_data, n_envs, mode, level_min, level_max, steps
 import sfo  # noqa: E402  (oracle binding; test infrastructure)
 
 
+def _trajectory_parity(torch, arena_data, n_envs, mode, level_min, level_max, steps, table, sample, player="account1",
+                       squad_agents=False, max_steps=0, with_obs=True):
+    """BASELINE.json-size batches at the survey's cadence: every arena of the batch plays
+    `steps` env-steps of the synthetic workload on the GPU with auto-reset, and for every arena the hash of
+    its canonical state after EVERY step is folded into a running checksum on the device
+    (chk = mix64(chk ^ hash)).  The C oracle plays the sampled arenas on all host cores
+    (sfo_run_trace) and must arrive at the same checksum, the same final state and, bit for bit, the
+    same final observation: one mismatch anywhere in a trajectory changes its checksum."""
+    from strikeforce_b200.sim import BatchedArena
+    kw = dict(mode=mode, level_min=level_min, level_max=level_max, squad_agents=squad_agents, max_steps=max_steps,
+              player=player)
+    sim = BatchedArena(n_envs, mode=mode, level=level_min, level_max=level_max, squad_agents=squad_agents,
+                       auto_reset=True, max_steps=max_steps, player=player)
+    try:
+        chk = torch.zeros(n_envs, dtype=torch.int64, device=sim.device)
+        for t in range(steps):
+            sim.step(sim.synth_actions(t, table))
+            chk = common.torch_mix64(torch, chk ^ sim.state_hash())
+        idx = torch.tensor(sample, device=sim.device)
+        got_chk = chk[idx].cpu().numpy().view(np.uint64)
+        got_last = sim.state_hash()[idx].cpu().numpy().view(np.uint64)
+        obs = sim.observe(1)[idx].reshape(len(sample), -1).cpu().numpy().view(np.uint32) if with_obs else None
+        stats = sim.stats()
+        ref = common.oracle_traces(kw, sample, steps, table, with_obs)
+        bad = [e for i, e in enumerate(sample) if np.uint64(ref[e][1]) != got_chk[i] or np.uint64(ref[e][2]) != got_last[i]]
+        assert not bad, "%d of %d trajectories differ from the oracle, first: arena %d" % (len(bad), len(sample), bad[0])
+        if with_obs:
+            for i, e in enumerate(sample):
+                if ref[e][3][0] != np.float32(-1.0).view(np.uint32):  # the player is alive: its agent sees
+                    assert (obs[i] == ref[e][3]).all(), "final observation differs: arena %d" % e
+        # the statistics the handle reduced on the device count every step of every arena
+        assert stats["steps"] + stats["overflows"] + stats["ub_guards"] == n_envs * steps
+        if len(sample) == n_envs:
+            assert stats["episodes"] == sum(r[0] for r in ref.values())
+        return stats
+    finally:
+        sim.close()
+
+
 def test_config2_solo_4096_every_arena(torch_cuda, arena_data):
-    """BASELINE.json configs[1]: Solo, 4,096 arenas on one GPU, random 9-symbol actions; EVERY arena
-    is compared with the CPU oracle after every step."""
-    _sampled_parity(torch_cuda, arena_data, 4096, sfcfg.MODE_SOLO, 1, 1, 40, sfcfg.ACTIONS9, list(range(4096)),
-                    obs_at=(39,))
+    """BASELINE.json configs[1]: Solo, 4,096 arenas on one GPU, random 9-symbol actions, 1,024 steps;
+    EVERY arena's whole trajectory is compared with the CPU oracle (4,096 x 1,024)."""
+    _trajectory_parity(torch_cuda, arena_data, 4096, sfcfg.MODE_SOLO, 1, 1, 1024, sfcfg.ACTIONS9, list(range(4096)))
+
+
+def test_config2_solo_4096_first_steps_lockstep(torch_cuda, arena_data):
+    """The same batch followed state for state (status, hash, observation) through its first steps."""
+    _sampled_parity(torch_cuda, arena_data, 4096, sfcfg.MODE_SOLO, 1, 1, 24, sfcfg.ACTIONS9, list(range(0, 4096, 16)),
+                    obs_at=(23,))
 
 
 def test_config3_timer_65536_sampled(torch_cuda, arena_data):
     """configs[2]: Timer mode, 65,536 arenas, consumables / throwables sheet, levels 1-10, 28-symbol
-    alphabet, observation tensors emitted on the device; 192 sampled arenas followed by the oracle."""
+    alphabet, observation tensors emitted on the device; the whole trajectories (768 steps) of 256 sampled
+    arenas against the oracle, plus a lock-step walk with observations over the first steps."""
     rng = np.random.default_rng(3)
-    sample = sorted(set(rng.integers(0, 65536, size=190).tolist()) | {0, 65535})
-    _sampled_parity(torch_cuda, arena_data, 65536, sfcfg.MODE_TIMER, 1, 10, 120, sfcfg.ACTIONS28, sample,
-                    player="synthetic", obs_at=(0, 119))
+    sample = sorted(set(rng.integers(0, 65536, size=254).tolist()) | {0, 65535})
+    _trajectory_parity(torch_cuda, arena_data, 65536, sfcfg.MODE_TIMER, 1, 10, 768, sfcfg.ACTIONS28, sample, player="synthetic")
+    _sampled_parity(torch_cuda, arena_data, 65536, sfcfg.MODE_TIMER, 1, 10, 40, sfcfg.ACTIONS28, sample[:64],
+                    player="synthetic", obs_at=(0, 39))
 
 
 def test_config4_squad_shard_131072_sampled(torch_cuda, arena_data):
-    """configs[3]: one GPU's shard (131,072 arenas) of the Squad 5v5 batch, blocks and portals in the
-    alphabet, levels 1-10; 160 sampled arenas followed by the oracle."""
+    """configs[3], the headline configuration: one GPU's shard (131,072 arenas) of the Squad 5v5 batch,
+    blocks and portals in the alphabet, levels 1-10, episodes truncated at 2,048 steps as in bench.py;
+    the whole 1,024-step trajectories of 512 sampled arenas and their final observations against the
+    oracle -- the populations the bench times (tens of humans, zombies, built cells) are reached well
+    inside that -- plus a lock-step walk over the first steps."""
     rng = np.random.default_rng(4)
-    sample = sorted(set(rng.integers(0, 131072, size=158).tolist()) | {0, 131071})
-    _sampled_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 100, sfcfg.ACTIONS28, sample)
+    sample = sorted(set(rng.integers(0, 131072, size=510).tolist()) | {0, 131071})
+    _trajectory_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 1024, sfcfg.ACTIONS28, sample, max_steps=2048)
+    _sampled_parity(torch_cuda, arena_data, 131072, sfcfg.MODE_SQUAD, 1, 10, 30, sfcfg.ACTIONS28, sample[:48])
 
 
 def test_config5_royale_32768_sampled(torch_cuda, arena_data):

@@ -306,14 +306,19 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic (seeded maps/seeds and splitmix64 action streams, include/sf_synth.h)",
-            "config": dict(WORKLOAD, envs_per_gpu=E, agents_per_env=A, prewarm_steps=args.prewarm,
-                           mean_population=dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"],
-                                                    [round(x, 2) for x in pop]))),
+            "config": dict(WORKLOAD, envs_per_gpu=E, agents_per_env=A),  # the same dict in both arms
+            "setup": {"prewarm_steps": args.prewarm,
+                      "mean_population": dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"],
+                                                  [round(x, 2) for x in pop])),
+                      "note": "untimed: arenas spread over episode ages before the timed steps"},
             "e2e": {"value": e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": E * A * world,
-                    "d2h_bytes_per_step": E * 32 * world, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": E * 32 * world, "ms_per_step": ms_e2e / K,
+                    "note": "sf_step_host: pinned host actions in, sf_step_out[n] back to the host every step; "
+                            "observations are device tensors by contract (the with_observation row) and are not copied"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic("sf_step_kernel", E), "peak_source": peak_src, "kernel": "sf_step_kernel<0>",
+                         "traffic": load_traffic("sf_step_kernel", E), "traffic_source": "profiles/traffic.json (ncu --set full of one launch of this workload)",
+                         "peak_source": peak_src, "kernel": "sf_step_kernel<0>",
                          "algo_bytes_per_launch": local_algo / K,
                          "algo_bytes_per_env_step": local_algo / max(1, K * E),
                          "note": "per GPU (rank 0); algorithmic bytes summed on the device from live populations"},
@@ -335,6 +340,130 @@ def run_ours(args):
                              "algo_bytes_per_observation": sfcfg.OBS_LEN * 4}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(args.cpu_steps)
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+ROYALE = dict(workload="royale16", mode="Royale (AI Battle Royale, gameplay.hpp:1235), 16 players in 4 teams, the reference's 3x30x100 map",
+              envs_per_gpu=32768, max_steps=2048, alphabet="agent actions \"+xzqeawsd\" sampled by the policy",
+              policy="AgentModel of bots/bot-0.5/Modules.hpp (random-init weights), fp32, one batched forward per tick",
+              l2="16 observations per arena = 64.5 GB per tick per GPU; no flush needed")
+
+
+def run_royale(args):
+    """BASELINE.json configs[4] on one GPU's shard: every tick builds the observations of all 16 players of
+    every arena on the device (sf_observe), runs ONE batched AgentModel forward over them, samples the 16
+    commands and steps -- nothing leaves the device.  `value` = env-steps/s of that whole tick; rows for
+    the step alone and step + observations explain it."""
+    import torch
+    import torch.distributed as dist
+
+    from strikeforce_b200 import bots, policy
+    from strikeforce_b200 import config as sfcfg
+    from strikeforce_b200 import dist as sfdist
+    from strikeforce_b200.sim import BatchedArena
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    torch.backends.cuda.matmul.allow_tf32 = False  # the reference network is fp32
+    torch.backends.cudnn.allow_tf32 = False
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    E = args.envs if args.envs != WORKLOAD["envs_per_gpu"] else ROYALE["envs_per_gpu"]
+    K, W = args.steps, args.warmup
+    teams = [1, 2, 3, 4] * 4
+    P = len(teams)
+    sim = BatchedArena(E, mode="Royale", teams=teams, auto_reset=True, max_steps=ROYALE["max_steps"], env_id_base=rank * E)
+    t = 0
+    for _ in range(min(args.prewarm, 512)):
+        sim.step(sim.synth_actions(t, sfcfg.ACTIONS28))
+        t += 1
+    torch.cuda.synchronize()
+    pop = sim.population().float().mean(0).tolist()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return sfdist.max_over_ranks(e0.elapsed_time(e1), sim.device) / n
+
+    acts = [sim.synth_actions(t + i, sfcfg.ACTIONS28, out=torch.empty((E, P), dtype=torch.uint8, device=sim.device))
+            for i in range(8)]
+    it = iter(range(10 ** 9))
+    ms_step = timed(lambda: sim.step(acts[next(it) % len(acts)]), 4 * K, W)
+    obs = torch.empty((E, P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32, device=sim.device)
+    mask = (1 << P) - 1
+    ms_observe = timed(lambda: sim.observe(mask, out=obs), 2 * K, W)
+    model = policy.AgentModel().to(sim.device)
+    agent = policy.PolicyAgent(model, E * P, device=sim.device, seed=1 + rank, chunk=args.policy_chunk, t_initial=0)
+    custom = bots.Custom(agent).prepare(sim)
+    actions = torch.empty((E, P), dtype=torch.uint8, device=sim.device)
+    l0 = sim.launches
+
+    def tick():
+        sim.observe(mask, out=obs)
+        with torch.no_grad():
+            idx = agent.predict(obs.view(E * P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN))
+        actions.copy_(custom._table[idx].view(E, P))
+        sim.step(actions)
+        custom.new_games(sim, sim.step_out()[:, 0] != sfcfg.RUNNING)
+
+    ms_tick = timed(tick, K, max(1, min(W, 2)))
+    launches = (sim.launches - l0) * K // (K + max(1, min(W, 2)))
+    # the public loop (bots.play): the same tick through the plugin surface; only the statistics reach the host
+    barrier()
+    w0 = time.perf_counter()
+    stats = bots.play(sim, custom, K)
+    barrier()
+    ms_play = sfdist.max_over_ranks((time.perf_counter() - w0) * 1e3, sim.device) / K
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+        peak, peak_src = load_peaks()
+        obs_bytes = E * P * sfcfg.OBS_LEN * 4
+        line = {
+            "metric": METRIC, "value": world * E / (ms_tick / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_tick, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (tick), fp32 (policy)",
+            "data": "synthetic (seeded matches, random-init policy weights)",
+            "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P),
+            "setup": {"prewarm_steps": min(args.prewarm, 512),
+                      "mean_population": dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"], [round(x, 2) for x in pop]))},
+            "e2e": {"value": world * E / (ms_play / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 128 // max(1, K),
+                    "ms_per_step": ms_play,
+                    "note": "bots.play: observe -> predict -> step through the plugin surface, wall clock; nothing but the "
+                            "final statistics reaches the host (observations arrive as device tensors by contract)"},
+            "gpu_launches": launches,
+            "rows": {"step_only": {"ms_per_step": ms_step, "env_steps_per_s": world * E / (ms_step / 1e3)},
+                     "sixteen_observations": {"ms": ms_observe, "GBps": obs_bytes / (ms_observe / 1e3) / 1e9},
+                     "agent_decisions_per_s": world * E * P / (ms_tick / 1e3)},
+            "roofline": {"bound": "hbm", "kernel": "sf_observe_kernel", "achieved": obs_bytes / (ms_observe / 1e3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": obs_bytes / (ms_observe / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algo_bytes_per_observation": sfcfg.OBS_LEN * 4,
+                         "note": "the simulator's dominant kernel of this workload; the tick itself is dominated by the fp32 policy forward (library convolutions)"},
+            "clocks": sampler.summary(),
+            "episodes": {k2: stats[k2] for k2 in ("episodes", "wins", "deaths", "truncated", "overflows", "ub_guards")},
+        }
         print(json.dumps(line))
     sim.close()
     if world > 1:
@@ -380,9 +509,15 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=8192, help="env-steps per host core per reference-arm step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-obs", action="store_true", help="skip the step+observation row")
+    ap.add_argument("--workload", default="squad5v5", choices=["squad5v5", "royale16"],
+                    help="squad5v5 = the headline (BASELINE.json configs[3]); royale16 = configs[4]: 16 players per arena, "
+                         "their observations and one batched policy forward every tick (use --steps 3)")
+    ap.add_argument("--policy-chunk", type=int, default=32768, help="royale16: observations per forward call")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "royale16":
+        run_royale(args)
     else:
         run_ours(args)
 

@@ -237,10 +237,9 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
 #define SF_OBS_LIST 976              /* entries per per-cell array (>= 961, keeps the arrays 16-byte aligned) */
 #define SF_OBS_BEYOND 0xFFFFu        /* code of a dynamic cell without a table row */
 #define SF_OBS_GROUP (SF_OBS_CELLS)  /* chunks per 4-channel group: 4 * 961 floats / 4 */
-#define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + 16)
+#define SF_OBS_WL (((SF_OBS_GROUP + SF_OBS_CTA - 1) / SF_OBS_CTA) * 32) /* chunks one warp looks at per window */
+#define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + (SF_OBS_CTA / 32) * SF_OBS_WL * 2 + 16)
 static_assert(SF_OBS_CELLS % 4 == 1 && SF_OBS_CH % 4 == 0, "the copy-out relies on 4 channels = 961 whole chunks");
-
-__device__ __forceinline__ void sf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 /* (arena, observed human slot) of work item `item` */
 __device__ __forceinline__ void sf_obs_item(int item, int nsel, uint32_t agent_mask, int *env, int *slot)
@@ -259,7 +258,8 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
     uint16_t *dlist = code + SF_OBS_LIST;                                     /* window index of dynamic cell i */
     int16_t *bmap = reinterpret_cast<int16_t *>(dlist + SF_OBS_LIST);
     int16_t *tmap = bmap + SF_OBS_LIST;
-    int *count = reinterpret_cast<int *>(tmap + SF_OBS_LIST);
+    uint16_t *worklist = reinterpret_cast<uint16_t *>(tmap + SF_OBS_LIST); /* [warp][SF_OBS_WL] chunks with content */
+    int *count = reinterpret_cast<int *>(worklist + (SF_OBS_CTA / 32) * SF_OBS_WL);
     SfTabs t;
     sf_global_tabs(d, t);
     uint32_t fb = 0;
@@ -276,23 +276,6 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         int env, slot;
         sf_obs_item(item, nsel, agent_mask, &env, &slot);
         float *out = obs + (size_t)item * SF_OBS_LEN;
-        /* The next window's header words are asked into L2 now and its cells when this window's
-           copy-out starts: by the time the CTA gets there they are a short trip away, and no
-           register has been held for them. */
-#ifdef SF_OBS_NO_PREFETCH /* A/B build */
-        const bool more = false;
-#else
-        const bool more = item + (int)gridDim.x < n_items;
-#endif
-        int env_n = 0, slot_n = 0;
-        if (more) {
-            sf_obs_item(item + gridDim.x, nsel, agent_mask, &env_n, &slot_n);
-            if (threadIdx.x == 0) {
-                sf_prefetch_l2(&d.misc[env_n]), sf_prefetch_l2(&d.mb[env_n]), sf_prefetch_l2(&d.mb[(size_t)d.E + env_n]);
-                sf_prefetch_l2(&d.ntemp[env_n]);
-                if (slot_n < k.cap_h) sf_prefetch_l2(&d.h_pw[(size_t)slot_n * d.E + env_n]), sf_prefetch_l2(&d.h_sel[(size_t)slot_n * d.E + env_n]);
-            }
-        }
         /* the few header words the features need */
         SfEnv e;
         const uint32_t misc = d.misc[env];
@@ -368,28 +351,40 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
 #pragma unroll
             for (int c = 0; c < SF_OBS_CH; ++c) feat[(16 + i) * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
         }
-        if (more) { /* the next window: its cells, the bullet and built-cell rows of its arena */
-            const uint32_t misc_n = d.misc[env_n]; /* in L2 by now */
-            if (slot_n < (int)((misc_n >> 16) & 0xFFu)) {
-                const int vcell_n = (int)(d.h_pw[(size_t)slot_n * d.E + env_n] & POS_CELL);
-#pragma unroll
-                for (int q = 0; q < PER; ++q) { /* one request per 64-byte overlay granule would do; neighbours merge */
-                    const int w = threadIdx.x + q * SF_OBS_CTA;
-                    const int cell = w < SF_OBS_CELLS ? sf_obs_cell(vcell_n, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
-                    if (cell >= 0 && ((cell & 31) == 0 || w % SF_OBS_WIN == 0 || (cell & 7) == 0))
-                        sf_prefetch_l2(&d.grid[(size_t)env_n * SF_GRID_STRIDE + (size_t)cell]);
-                }
-                if (threadIdx.x < SF_LIM_BULLETS && threadIdx.x < (unsigned)k.cap_b) {
-                    sf_prefetch_l2(&d.b_meta[(size_t)threadIdx.x * d.E + env_n]);
-                    sf_prefetch_l2(&d.b_pw[(size_t)threadIdx.x * d.E + env_n]);
-                }
-                if (threadIdx.x < 8) sf_prefetch_l2(&d.t_cell[(size_t)env_n * d.cap_t + threadIdx.x * 32]);
-            }
-        }
         __syncthreads();
-        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM */
+        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM.  Two passes
+           per warp, so that the lanes of a warp do the same thing: first every chunk is looked at and
+           the all-zero ones (two thirds) are stored right away, the others go to the warp's work list;
+           then the listed chunks are assembled from the table with all lanes busy. */
         float4 *dst = reinterpret_cast<float4 *>(out);
-        for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
+        const unsigned lane = threadIdx.x & 31u;
+        uint16_t *wl = worklist + (threadIdx.x >> 5) * SF_OBS_WL;
+        int n_wl = 0;
+        for (int q0 = (int)(threadIdx.x & ~31u); q0 < SF_OBS_GROUP; q0 += SF_OBS_CTA) {
+            const int q = q0 + (int)lane;
+            bool busy = false;
+            if (q < SF_OBS_GROUP) {
+                int w = 4 * q - ((4 * q) / SF_OBS_CELLS) * SF_OBS_CELLS;
+                uint32_t any = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    any |= code[w];
+                    if (++w == SF_OBS_CELLS) w = 0;
+                }
+                busy = any != 0;
+                if (!busy) {
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int g = 0; g < SF_OBS_CH / 4; ++g) __stcs(dst + g * SF_OBS_GROUP + q, zero);
+                }
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, busy);
+            if (busy) wl[n_wl + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)q;
+            n_wl += __popc(mb);
+        }
+        __syncwarp();
+        for (int i = (int)lane; i < n_wl; i += 32) {
+            const int q = wl[i];
             int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
             int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
             bool beyond = false;
@@ -428,6 +423,7 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                     __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
             }
         }
+        __syncwarp(); /* the list is rewritten for the next window */
     }
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }

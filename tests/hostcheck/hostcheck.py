@@ -13,30 +13,34 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 from strikeforce_b200 import config as sfcfg  # noqa: E402
 
-# HOSTCHECK_CFLAGS builds a variant next to the default one (e.g. "-DSF_BF_WORDS=1": a bullet-flag
-# filter so small that nearly every look-up takes the confirming walk over the bullets)
-EXTRA = os.environ.get("HOSTCHECK_CFLAGS", "").split()
-LIB_PATH = os.path.join(HERE, "libhostcheck%s.so" % ("_" + "".join(c for c in "".join(EXTRA) if c.isalnum()) if EXTRA else ""))
-_lib = None
+# extra compiler flags build a variant next to the default one (e.g. "-DSF_BT_SLOTS=7 -DSF_BT_FULL=5": a
+# bullet-flag table so small that most flags spill into the overlay); HOSTCHECK_CFLAGS sets the default variant
+EXTRA = tuple(os.environ.get("HOSTCHECK_CFLAGS", "").split())
+_libs = {}
 
 
-def build(force=False):
+def lib_path(extra=EXTRA):
+    tag = "_" + "".join(c for c in "".join(extra) if c.isalnum()) if extra else ""
+    return os.path.join(HERE, "libhostcheck%s.so" % tag)
+
+
+def build(force=False, extra=EXTRA):
     srcs = [os.path.join(HERE, "hostcheck.cpp")] + [
         os.path.join(ROOT, "strikeforce_b200", "csrc", f)
         for f in ("sf_core.cuh", "sf_canon_dev.cuh", "sf_host_setup.h", "sf_state.h", "sf_obs.cuh")]
-    if not force and os.path.exists(LIB_PATH) and all(
-            os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    path = lib_path(extra)
+    if not force and os.path.exists(path) and all(os.path.getmtime(path) >= os.path.getmtime(s) for s in srcs):
         return
     subprocess.check_call([
         "g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
-        "-I" + os.path.join(ROOT, "strikeforce_b200", "csrc")] + EXTRA + ["-x", "c++", srcs[0], "-o", LIB_PATH])
+        "-I" + os.path.join(ROOT, "strikeforce_b200", "csrc")] + list(extra) + ["-x", "c++", srcs[0], "-o", path])
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = C.CDLL(LIB_PATH)
+def lib(extra=EXTRA):
+    extra = tuple(extra)
+    if extra not in _libs:
+        build(extra=extra)
+        L = C.CDLL(lib_path(extra))
         L.hc_create.argtypes = [C.POINTER(sfcfg.SfConfig)]
         L.hc_create.restype = C.c_void_p
         L.hc_destroy.argtypes = [C.c_void_p]
@@ -56,61 +60,62 @@ def lib():
         L.hc_compute_damage.argtypes = [C.c_int, C.c_int]
         L.hc_obs_transform_milli.argtypes = [C.c_int]
         L.hc_obs_transform_milli.restype = C.c_float
-        _lib = L
-    return _lib
+        _libs[extra] = L
+    return _libs[extra]
 
 
 class HostSim:
-    def __init__(self, cfg):
+    def __init__(self, cfg, extra=EXTRA):
         self._cfg = cfg
-        self._h = lib().hc_create(C.byref(cfg))
+        self._lib = lib(extra)
+        self._h = self._lib.hc_create(C.byref(cfg))
         if not self._h:
             raise RuntimeError("hc_create failed")
         self.n_envs = cfg.n_envs
-        self.n_agents = lib().hc_n_agents(self._h)
+        self.n_agents = self._lib.hc_n_agents(self._h)
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().hc_destroy(self._h)
+            self._lib.hc_destroy(self._h)
             self._h = None
 
     def reset(self, env, tb, serial):
-        lib().hc_reset(self._h, env, tb, serial)
+        self._lib.hc_reset(self._h, env, tb, serial)
 
     def step(self, actions, half=0):
         a = None if actions is None else bytes(actions)
         if a is not None:
             assert len(a) == self.n_envs * self.n_agents
-        lib().hc_step(self._h, a, half)
+        self._lib.hc_step(self._h, a, half)
 
     def dump(self, env):
         buf = np.empty(1 << 18, dtype=np.int32)
-        n = lib().hc_dump(self._h, env, buf.ctypes.data, buf.size)
+        n = self._lib.hc_dump(self._h, env, buf.ctypes.data, buf.size)
         assert n >= 0
         return buf[:n].copy()
 
     def state_hash(self, env):
-        return int(lib().hc_hash(self._h, env))
+        return int(self._lib.hc_hash(self._h, env))
 
     def status(self, env):
-        return lib().hc_status(self._h, env)
+        return self._lib.hc_status(self._h, env)
 
     def misc(self, env):
         """the packed header word (sf_state.h SfDev::misc)"""
-        return lib().hc_misc(self._h, env)
+        return self._lib.hc_misc(self._h, env)
 
     def step_out(self, env):
         o = sfcfg.StepOut()
-        lib().hc_step_out(self._h, env, C.byref(o))
+        self._lib.hc_step_out(self._h, env, C.byref(o))
         return {n: getattr(o, n) for n, _ in sfcfg.StepOut._fields_}
 
     def observe(self, env, slot=0, raw=False):
         out = np.empty(sfcfg.OBS_LEN, dtype=np.float32)
-        if lib().hc_observe(self._h, env, slot, out.ctypes.data, int(raw)) != sfcfg.OBS_LEN:
+        if self._lib.hc_observe(self._h, env, slot, out.ctypes.data, int(raw)) != sfcfg.OBS_LEN:
             raise RuntimeError("no such human slot")
         return out
 
     def stats(self):
         out = np.zeros(16, dtype=np.uint64)
-        lib().hc_stats(self._h, out.ctypes.data)
+        self._lib.hc_stats(self._h, out.ctypes.data)
         return dict(zip(sfcfg.STAT_NAMES, out.astype(np.int64).tolist()))

@@ -176,3 +176,38 @@ def test_royale_auto_reset_follows_the_seed_chain(arena_data):
             d0, d1 = o.dump(), hs.dump(e)
             assert len(d0) == len(d1) and (d0 == d1).all(), sfo.diff_records(d0, d1)
     assert hs.stats()["episodes"] == sum(episode) == 9
+
+
+SPILL_STRESS = ("-DSF_BT_SLOTS=7", "-DSF_BT_FULL=5")  # a bullet-flag table that overflows all the time
+
+
+@pytest.mark.parametrize("mode,extra", [(sfcfg.MODE_SQUAD, ()), (sfcfg.MODE_SQUAD, SPILL_STRESS), (sfcfg.MODE_TIMER, SPILL_STRESS)],
+                         ids=["squad", "squad-tiny-flag-table", "timer-tiny-flag-table"])
+def test_soak_against_the_oracle(arena_data, mode, extra):
+    """Long episodes with auto-reset, levels 1-10, the whole 28-symbol alphabet: the populations the
+    benchmark times (tens of humans, zombies and bullets, portals, built cells) and the paths only they
+    reach -- bullets over exits, radiation taking a cell's flag over, absorbed bullets, a full flag
+    table spilling into the overlay (the tiny-table builds do that constantly).  State hash and step
+    status against the C oracle after every step."""
+    n, steps, base = 12, 1300, 2000
+    cfg = sfcfg.make_config(arena_data, n_envs=n, mode=mode, level_min=1, level_max=10, auto_reset=True, max_steps=1024,
+                            env_id_base=base)
+    hs = hostcheck.HostSim(cfg, extra=extra)
+    oracles = []
+    for e in range(n):
+        lvl = 1 + (base + e) % 10
+        o = sfo.Arena(sfcfg.make_config(arena_data, mode=mode, level_min=lvl, max_steps=1024))
+        o.reset(lvl, common.synth_tb(base + e), common.synth_serial(base + e, 0))
+        oracles.append(o)
+    episode = [0] * n
+    for t in range(steps):
+        act = common.synth_actions(range(base, base + n), 1, t, sfcfg.ACTIONS28)
+        hs.step(act.tobytes())
+        for e, o in enumerate(oracles):
+            st = o.step(bytes(act[e]))
+            assert hs.step_out(e)["status"] == st, "status: step %d arena %d" % (t, e)
+            if st != sfcfg.RUNNING:
+                episode[e] += 1
+                o.reset(1 + (base + e) % 10, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
+            assert np.uint64(hs.state_hash(e)) == np.uint64(o.state_hash()), "state: step %d arena %d" % (t, e)
+    assert sum(episode) >= n  # every arena went through at least one truncation and reset

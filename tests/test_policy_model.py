@@ -8,6 +8,7 @@ import os
 import struct
 
 import numpy as np
+import pytest
 import torch
 
 from strikeforce_b200.policy import AgentModel, PolicyAgent
@@ -134,3 +135,31 @@ def test_policy_agent_follows_the_reference_agent_around_the_network():
     draws = torch.stack([b.predict(x) for _ in range(400)])
     frac0 = float((draws == 0).float().mean())
     assert 0.44 < frac0 < 0.56, frac0
+
+
+@pytest.mark.gpu
+def test_cuda_forward_matches_the_reference_network():
+    """The forward the policy loop actually runs -- batched, on the B200, cuDNN / cuBLAS kernels --
+    against the reference's own AgentModel (policy_golden.bin).  fp32 with TF32 off; tolerance 5e-6
+    absolute on probabilities and values (the reduction orders of the GPU kernels differ from the
+    reference's single-sample CPU kernels).  Row 1 of a batch of 64 replays the golden sequence, the
+    other rows see other inputs: rows must not leak into each other."""
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = read_golden()
+    steps = len([k for k in g if k.startswith("p:")])
+    dev = torch.device("cuda", 0)
+    m = formula_model().to(dev)
+    B = 64
+    st = m.initial_state(B, dev)
+    worst = 0.0
+    with torch.no_grad():
+        for s in range(steps):
+            x = torch.cat([formula_obs(s + 3 * r) if r != 1 else formula_obs(s) for r in range(B)]).to(dev)
+            p, v, st = m(x, st)
+            worst = max(worst, float(np.abs(p[1].cpu().numpy() - g["p:%d" % s]).max()),
+                        float(np.abs(v[1].cpu().numpy() - g["v:%d" % s]).max()))
+            act = torch.tensor([(s + r) % 9 if r != 1 else (s * 4 + 1) % 9 for r in range(B)], device=dev)
+            st = AgentModel.with_action(st, act)
+    assert worst < 5e-6, "CUDA forward differs from the reference network by %g" % worst

@@ -15,6 +15,8 @@ import numpy as np
 from . import data as sfdata
 
 ABI_VERSION = 2
+FLOORS, ROWS, COLS = 3, 30, 100  # SF_FLOORS / SF_ROWS / SF_COLS (gameplay.hpp:37)
+CELLS = FLOORS * ROWS * COLS
 OBS_CH, OBS_WIN = 32, 31
 OBS_LEN = OBS_CH * OBS_WIN * OBS_WIN
 SHEET_LEN = sfdata.SHEET_LEN
@@ -143,3 +145,15 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
         cfg.level_min = cfg.level_max = 1  # gameplay.hpp:1641, 1659
     cfg._keep = (cells, portal)
     return cfg
+
+
+def dump_config(cfg: SfConfig, path):
+    """Write ``cfg`` as the blob the C++ host reads (strikeforce_b200/host/bot-b200/Custom.hpp,
+    ``sfb200::Config::load``): the struct as it lies in memory, then map_cells[CELLS] (uint8), then
+    map_portal[CELLS] (int16).  The two pointers inside the struct are meaningless in the file."""
+    cells = np.ctypeslib.as_array(cfg.map_cells, shape=(CELLS,)).astype(np.uint8)
+    portal = np.ctypeslib.as_array(cfg.map_portal, shape=(CELLS,)).astype(np.int16)
+    with open(path, "wb") as f:
+        f.write(bytes(cfg))
+        f.write(cells.tobytes())
+        f.write(portal.tobytes())

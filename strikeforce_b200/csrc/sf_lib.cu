@@ -211,7 +211,7 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
  * shared memory: it builds a small description of the window and then streams the 7,688 16-byte
  * chunks of the observation straight from registers with plain coalesced stores (512 contiguous
  * bytes per warp instruction; a store holds no resource of the CTA once it has issued, and 25 KB
- * of shared memory per CTA leave room for 7 CTAs per SM).
+ * of shared memory per CTA leave room for 8 CTAs per SM).
  *   1. entity -> window maps for the owning bullets and player-built cells (shared memory);
  *   2. the window is classified into a CODE per cell: 0 = nothing to show (floor, outside the map),
  *      1..15 = the static flags of a cell with nothing on it (wall, stairs, exit), 16 + i = the
@@ -227,18 +227,17 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
 #define SF_OBS_CTA 128
 #endif
 #ifndef SF_OBS_CTAS_PER_SM
-#define SF_OBS_CTAS_PER_SM 7
+#define SF_OBS_CTAS_PER_SM 8
 #endif
 #ifndef SF_OBS_CACHE
-#define SF_OBS_CACHE 144 /* dynamic cells with a table row; any beyond are described again during the copy-out */
+#define SF_OBS_CACHE 112 /* dynamic cells with a table row; any beyond are described again during the copy-out */
 #endif
 #define SF_OBS_ROWS (16 + SF_OBS_CACHE)
 #define SF_OBS_PITCH (SF_OBS_CH + 1) /* floats per table row: odd, so that rows fall into different banks */
 #define SF_OBS_LIST 976              /* entries per per-cell array (>= 961, keeps the arrays 16-byte aligned) */
 #define SF_OBS_BEYOND 0xFFFFu        /* code of a dynamic cell without a table row */
 #define SF_OBS_GROUP (SF_OBS_CELLS)  /* chunks per 4-channel group: 4 * 961 floats / 4 */
-#define SF_OBS_WL (((SF_OBS_GROUP + SF_OBS_CTA - 1) / SF_OBS_CTA) * 32) /* chunks one warp looks at per window */
-#define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + (SF_OBS_CTA / 32) * SF_OBS_WL * 2 + 16)
+#define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + 16)
 static_assert(SF_OBS_CELLS % 4 == 1 && SF_OBS_CH % 4 == 0, "the copy-out relies on 4 channels = 961 whole chunks");
 
 /* (arena, observed human slot) of work item `item` */
@@ -258,8 +257,7 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
     uint16_t *dlist = code + SF_OBS_LIST;                                     /* window index of dynamic cell i */
     int16_t *bmap = reinterpret_cast<int16_t *>(dlist + SF_OBS_LIST);
     int16_t *tmap = bmap + SF_OBS_LIST;
-    uint16_t *worklist = reinterpret_cast<uint16_t *>(tmap + SF_OBS_LIST); /* [warp][SF_OBS_WL] chunks with content */
-    int *count = reinterpret_cast<int *>(worklist + (SF_OBS_CTA / 32) * SF_OBS_WL);
+    int *count = reinterpret_cast<int *>(tmap + SF_OBS_LIST);
     SfTabs t;
     sf_global_tabs(d, t);
     uint32_t fb = 0;
@@ -352,39 +350,11 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             for (int c = 0; c < SF_OBS_CH; ++c) feat[(16 + i) * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
         }
         __syncthreads();
-        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM.  Two passes
-           per warp, so that the lanes of a warp do the same thing: first every chunk is looked at and
-           the all-zero ones (two thirds) are stored right away, the others go to the warp's work list;
-           then the listed chunks are assembled from the table with all lanes busy. */
+        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM; every store
+           instruction of a warp covers 512 contiguous bytes (storing the all-zero chunks first and the
+           others in a second pass, lane-dense, was measured 40% SLOWER: partial-warp stores) */
         float4 *dst = reinterpret_cast<float4 *>(out);
-        const unsigned lane = threadIdx.x & 31u;
-        uint16_t *wl = worklist + (threadIdx.x >> 5) * SF_OBS_WL;
-        int n_wl = 0;
-        for (int q0 = (int)(threadIdx.x & ~31u); q0 < SF_OBS_GROUP; q0 += SF_OBS_CTA) {
-            const int q = q0 + (int)lane;
-            bool busy = false;
-            if (q < SF_OBS_GROUP) {
-                int w = 4 * q - ((4 * q) / SF_OBS_CELLS) * SF_OBS_CELLS;
-                uint32_t any = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    any |= code[w];
-                    if (++w == SF_OBS_CELLS) w = 0;
-                }
-                busy = any != 0;
-                if (!busy) {
-                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int g = 0; g < SF_OBS_CH / 4; ++g) __stcs(dst + g * SF_OBS_GROUP + q, zero);
-                }
-            }
-            const unsigned mb = __ballot_sync(0xffffffffu, busy);
-            if (busy) wl[n_wl + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)q;
-            n_wl += __popc(mb);
-        }
-        __syncwarp();
-        for (int i = (int)lane; i < n_wl; i += 32) {
-            const int q = wl[i];
+        for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
             int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
             int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
             bool beyond = false;
@@ -423,7 +393,6 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                     __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
             }
         }
-        __syncwarp(); /* the list is rewritten for the next window */
     }
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }

@@ -46,9 +46,11 @@ UNIT = "env-steps/s"
 
 def _ref_worker(args):
     """One process = one arena of the unmodified reference (its state is global)."""
-    env, level, n_steps, with_obs = args
+    env, level, n_steps, with_obs, noguard = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sfref
+    if noguard:
+        sfref.LIB_PATH = sfref.NOGUARD_PATH
     from strikeforce_b200 import config as sfcfg
     caps = [sfcfg.DEFAULT_CAPS[k] for k in ("cap_humans", "cap_zombies", "cap_bullets", "cap_chests", "cap_built",
                                             "cap_portals")]
@@ -60,7 +62,7 @@ def _ref_worker(args):
 
 
 def _port_worker(args):
-    env, level, n_steps, with_obs = args
+    env, level, n_steps, with_obs, _ = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sfo
     from strikeforce_b200 import config as sfcfg
@@ -73,7 +75,7 @@ def _port_worker(args):
     return n, time.perf_counter() - t0
 
 
-def cpu_reference(steps_per_arena, passes=1, with_obs=False):
+def cpu_reference(steps_per_arena, passes=1, with_obs=False, overhead=False):
     """Times the reference's own CPU implementation on all host cores.  Returns a dict for
     the `cpu_baseline` key.  Each arena plays one full truncated episode cycle per pass, the
     same age mix the GPU arm sees."""
@@ -82,7 +84,7 @@ def cpu_reference(steps_per_arena, passes=1, with_obs=False):
     cores = os.cpu_count() or 1
     kind = "reference" if sfref.available() else "port"
     worker = _ref_worker if kind == "reference" else _port_worker
-    jobs = [(e, 1 + e % 10, steps_per_arena, with_obs) for e in range(cores * passes)]
+    jobs = [(e, 1 + e % 10, steps_per_arena, with_obs, False) for e in range(cores * passes)]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -91,10 +93,22 @@ def cpu_reference(steps_per_arena, passes=1, with_obs=False):
     total = sum(n for n, _ in res)
     busy = sum(t for _, t in res)
     span = max(t for _, t in res) * passes  # all cores run side by side; process start-up excluded
-    return dict(value=total / span, unit=UNIT, cores=cores, kind=kind, per_core=total / busy,
-                sample="%d arenas (one process each, %d at a time) x %d steps of squad5v5 incl. auto-reset; "
-                       "%.1f s of stepping, %.1f s wall with process start-up" % (len(jobs), cores, steps_per_arena,
-                                                                                 span, wall))
+    out = dict(value=total / span, unit=UNIT, cores=cores, kind=kind, per_core=total / busy,
+               sample="%d arenas (one process each, %d at a time) x %d steps of squad5v5 incl. auto-reset; "
+                      "%.1f s of stepping, %.1f s wall with process start-up" % (len(jobs), cores, steps_per_arena,
+                                                                                span, wall))
+    if overhead and kind == "reference" and os.path.exists(sfref.NOGUARD_PATH):
+        # what the harness's own checks cost (capacity tracking after every phase, the out-of-bounds scan
+        # before update_bull: oracle/ref_harness/harness.cpp): the same arenas with the checks compiled out
+        q = max(1024, steps_per_arena // 4)
+        with ctx.Pool(cores) as pool:
+            r1 = pool.map(worker, [(e, 1 + e % 10, q, with_obs, False) for e in range(cores)], chunksize=1)
+        with ctx.Pool(cores) as pool:
+            r0 = pool.map(worker, [(e, 1 + e % 10, q, with_obs, True) for e in range(cores)], chunksize=1)
+        g1, g0 = sum(n for n, _ in r1) / sum(t for _, t in r1), sum(n for n, _ in r0) / sum(t for _, t in r0)
+        out["harness_overhead"] = {"per_core_with_checks": g1, "per_core_without_checks": g0, "slowdown_from_checks": g0 / g1,
+                                   "sample": "%d arenas x %d steps each way" % (cores, q)}
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -339,7 +353,7 @@ def run_ours(args):
                              "traffic": load_traffic("sf_observe_kernel", E),
                              "algo_bytes_per_observation": sfcfg.OBS_LEN * 4}}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_reference(args.cpu_steps)
+            line["cpu_baseline"] = cpu_reference(args.cpu_steps, overhead=True)
         print(json.dumps(line))
     sim.close()
     if world > 1:
@@ -371,8 +385,12 @@ def run_royale(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
-    torch.backends.cuda.matmul.allow_tf32 = False  # the reference network is fp32
-    torch.backends.cudnn.allow_tf32 = False
+    # the reference network is fp32 (libtorch on the CPU); here the linear layers and GRUs stay fp32 and the
+    # convolutions run as cuDNN runs them by default on this GPU (TF32 tensor-core math, fp32 accumulate):
+    # strict fp32 convolutions are 8x slower (4.4 s per tick, profiles/) and the policy is sampled anyway.
+    # The parity tests of the network (tests/test_policy_model.py, test_cpp_host.py) run with TF32 off.
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = not args.strict_fp32
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E = args.envs if args.envs != WORKLOAD["envs_per_gpu"] else ROYALE["envs_per_gpu"]
@@ -444,7 +462,7 @@ def run_royale(args):
         obs_bytes = E * P * sfcfg.OBS_LEN * 4
         line = {
             "metric": METRIC, "value": world * E / (ms_tick / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_tick, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (tick), fp32 (policy)",
+            "ms_per_step": ms_tick, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (tick), fp32 policy" + ("" if args.strict_fp32 else " with TF32 convolutions (cuDNN default)"),
             "data": "synthetic (seeded matches, random-init policy weights)",
             "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P),
             "setup": {"prewarm_steps": min(args.prewarm, 512),
@@ -513,6 +531,7 @@ def main():
                     help="squad5v5 = the headline (BASELINE.json configs[3]); royale16 = configs[4]: 16 players per arena, "
                          "their observations and one batched policy forward every tick (use --steps 3)")
     ap.add_argument("--policy-chunk", type=int, default=32768, help="royale16: observations per forward call")
+    ap.add_argument("--strict-fp32", action="store_true", help="royale16: convolutions without TF32 (8x slower)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

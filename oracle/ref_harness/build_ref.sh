@@ -35,4 +35,9 @@ cp -f "$REF/accounts/game/1/info, 1.txt" "$OUT/rundir/accounts/game/1/info, 1.tx
 g++ -std=c++17 -O2 -fPIC -shared -w \
     -I"$OUT/build" -I"$HERE/stubs" -I"$ROOT/include" \
     "$HERE/harness.cpp" -o "$OUT/libsfref.so" -lpthread
+# the same engine without the harness's capacity / out-of-bounds checks: bench.py times both and reports
+# what the checks cost (they are the harness's, not the reference's)
+g++ -std=c++17 -O2 -fPIC -shared -w -DSFREF_NO_GUARDS \
+    -I"$OUT/build" -I"$HERE/stubs" -I"$ROOT/include" \
+    "$HERE/harness.cpp" -o "$OUT/libsfref_noguard.so" -lpthread
 echo "built $OUT/libsfref.so"

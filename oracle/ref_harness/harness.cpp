@@ -288,8 +288,13 @@ int sfref_status() { return g_status; }
 int sfref_step(const unsigned char *actions, int n)
 {
     if (g_status != SF_RUNNING) return g_status;
+#ifdef SFREF_NO_GUARDS /* timing build (libsfref_noguard.so): what the harness's own checks cost the CPU baseline */
+#define SF_CHECK() ((void)0)
+#define SF_UBGUARD() ((void)0)
+#else
 #define SF_CHECK() do { track_and_check_caps(); if (g_status != SF_RUNNING) return g_status; } while (0)
 #define SF_UBGUARD() do { if (update_bull_would_go_out_of_bounds()) { g_status = SF_UB_GUARD; return g_status; } } while (0)
+#endif
     if (g.frame % g.pc <= 1) g.spawn_chest();
     if (g.frame % g.pz <= 1) g.spawn_zombie_npc();
     if (g.frame % g.ph <= 1) g.spawn_human_npc();

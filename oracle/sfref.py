@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_ref", "libsfref.so")
+LIB_PATH = os.environ.get("SFREF_LIB") or os.path.join(HERE, "_ref", "libsfref.so")
+NOGUARD_PATH = os.path.join(HERE, "_ref", "libsfref_noguard.so")  # timing build: the harness's own checks compiled out
 RUNDIR = os.path.join(HERE, "_ref", "rundir")
 ACCOUNT1 = os.path.join(RUNDIR, "player_account1.txt")
 OBS_LEN = 32 * 31 * 31

@@ -93,12 +93,51 @@ def write_royale(path, tb, serial, sheets, teams, commands, ind=0):
             f.write(chr(c) + "\n")
 
 
+@dataclass
+class RoyaleLog:
+    server: tuple       # the three tokens of the server line (ip, port, password)
+    tb: int
+    serial: int
+    ind: int
+    teams: list          # team of every player, slot order
+    names: list
+    sheets: np.ndarray   # int32 [players, 32], slot order, as stored in the file
+    commands: bytes      # the command symbols in file order
+
+
+def read_royale(path):
+    """The reader of ``write_royale``: an online match as the reference's replay mode consumes it
+    (gameplay.hpp:1762-1806) -- the server line, the seeds, ``players ind team``, the sheet of ``ind``,
+    then sheet and team of every other player in slot order, then the commands."""
+    with open(path, "rb") as f:
+        tok = f.read().decode("latin-1").split()
+    server = tuple(tok[:3])
+    tb, serial, players, ind, team = (int(t) for t in tok[3:8])
+    if not (2 <= players <= 64 and 0 <= ind < players):
+        raise ValueError("%s: not an online match log (players %d, ind %d)" % (path, players, ind))
+    pos = 8
+    names, sheets, teams = [None] * players, np.zeros((players, sfdata.SHEET_LEN), dtype=np.int32), [0] * players
+    for i in [ind] + [j for j in range(players) if j != ind]:
+        names[i] = tok[pos]
+        sheets[i] = [int(t) for t in tok[pos + 1:pos + 1 + sfdata.SHEET_LEN]]
+        pos += 1 + sfdata.SHEET_LEN
+        if i == ind:
+            teams[i] = team
+        else:
+            teams[i] = int(tok[pos])
+            pos += 1
+    return RoyaleLog(server, tb, serial, ind, teams, names, sheets, "".join(tok[pos:]).encode("latin-1"))
+
+
 def read(path):
-    """Parse a log the way the reference's stream extraction does (whitespace separated tokens;
-    every command is one non-blank character)."""
+    """Parse an OFFLINE log the way the reference's stream extraction does (whitespace separated
+    tokens; every command is one non-blank character).  Online match files start with the server
+    line and are read by ``read_royale``."""
     with open(path, "rb") as f:
         text = f.read().decode("latin-1")
     tok = text.split()
+    if not tok[0].lstrip("-").isdigit():
+        raise ValueError("%s starts with %r: an online match log, use read_royale" % (path, tok[0]))
     tb, serial, players, ind, team = (int(t) for t in tok[:5])
     name = tok[5]
     sheet = np.array([int(t) for t in tok[6:6 + sfdata.SHEET_LEN]], dtype=np.int32)

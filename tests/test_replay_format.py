@@ -82,3 +82,20 @@ def test_reference_replays_our_file_like_the_oracle(arena_data, tmp_path, mode, 
             break
         d0, d1 = sfref.dump(), o.dump()
         assert len(d0) == len(d1) and (d0 == d1).all(), "step %d: %s" % (t, sfo.diff_records(d0, d1))
+
+
+def test_royale_log_round_trip(tmp_path, arena_data):
+    """write_royale -> read_royale: the online replay format (gameplay.hpp:1762-1806) has a reader too."""
+    import pytest
+    from strikeforce_b200 import replay
+    rng = np.random.default_rng(9)
+    teams = [2, 1, 3, 1, 2]
+    sheets = np.stack([np.asarray(arena_data.player_sheet("account1"), dtype=np.int32) + i for i in range(5)])
+    cmds = bytes(sfcfg.ACTIONS28[j] for j in rng.integers(28, size=97))
+    path = tmp_path / "online.sf_sample"
+    replay.write_royale(str(path), 1700000321, 987654, sheets, teams, cmds, ind=2)
+    log = replay.read_royale(str(path))
+    assert (log.tb, log.serial, log.ind, log.teams) == (1700000321, 987654, 2, teams)
+    assert (log.sheets == sheets).all() and log.commands == cmds and log.names[2] == "player2"
+    with pytest.raises(ValueError):
+        replay.read(str(path))  # the offline reader refuses it instead of folding sheets into commands

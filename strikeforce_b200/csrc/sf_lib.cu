@@ -378,6 +378,7 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             } else { /* more dynamic cells than table rows (rare): those are described here, once per chunk */
                 float val[4][SF_OBS_CH / 4];
                 int cj = (4 * q) / SF_OBS_CELLS, wj = 4 * q - cj * SF_OBS_CELLS;
+#pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     if (row[j] <= -2) {
                         const int cell = sf_obs_cell(vcell, wj / SF_OBS_WIN, wj % SF_OBS_WIN);

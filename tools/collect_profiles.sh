@@ -1,28 +1,44 @@
 #!/bin/bash
 # usage: bash tools/collect_profiles.sh <tag>  -- turn gpurun_out/<tag>_* (tools/gpu_final.sh) into the tracked files under profiles/
 set -e
-TAG=${1:-r01}
+TAG=${1:-r02}
 cd "$(dirname "$0")/.."
 cp gpurun_out/${TAG}_bench.json profiles/${TAG}_bench.json
 cp gpurun_out/${TAG}_bench_reference.json profiles/${TAG}_bench_reference.json
 cp gpurun_out/${TAG}_launches.csv profiles/${TAG}_launches.csv
+cp gpurun_out/${TAG}_tests.log profiles/${TAG}_gpu_tests.log 2>/dev/null || true
 ncu -i gpurun_out/${TAG}_step.ncu-rep --page source --print-source cuda,sass --csv 2>/dev/null > /tmp/${TAG}_src_step.csv
 ncu -i gpurun_out/${TAG}_obs.ncu-rep --page source --print-source cuda,sass --csv 2>/dev/null > /tmp/${TAG}_src_obs.csv
 {
-  echo "# ncu --set full, sf_step_kernel<0>, 131072 arenas, steady-state populations (bench.py --steps 2 --warmup 1 --prewarm 1536 --no-cpu)"
+  echo "# ncu --set full of ONE sf_step_kernel<0> launch inside the timed region of the bench command itself"
+  echo "# (tools/gpu_final.sh: python bench.py --steps 20 --warmup 3 --no-cpu, NVTX range sf_timed_device): 131,072 arenas,"
+  echo "# the populations the bench times"
   python tools/ncu_summary.py gpurun_out/${TAG}_step.ncu-rep
+  echo; echo "# stall reasons (share of the warp samples)"
+  python tools/ncu_stalls.py gpurun_out/${TAG}_step.ncu-rep
   echo; echo "# per function (samples, warp instructions, average active lanes)"
   python tools/ncu_funcs.py /tmp/${TAG}_src_step.csv strikeforce_b200/csrc/sf_core.cuh 2>/dev/null
   echo; echo "# hottest source lines"
   python tools/ncu_lines.py /tmp/${TAG}_src_step.csv 30
 } > profiles/${TAG}_step_kernel_ncu.txt
 {
-  echo "# ncu --set full, sf_observe_kernel, 131072 observations"
+  echo "# ncu --set full of ONE sf_observe_kernel launch inside the timed region of the bench command (NVTX range sf_timed_observe), 131,072 observations"
   python tools/ncu_summary.py gpurun_out/${TAG}_obs.ncu-rep
+  echo; echo "# stall reasons (share of the warp samples)"
+  python tools/ncu_stalls.py gpurun_out/${TAG}_obs.ncu-rep
   echo; python tools/ncu_lines.py /tmp/${TAG}_src_obs.csv 15
 } > profiles/${TAG}_observe_kernel_ncu.txt
 ncu -i gpurun_out/${TAG}_step.ncu-rep --page raw --csv 2>/dev/null > profiles/${TAG}_step_kernel_raw.csv
 ncu -i gpurun_out/${TAG}_obs.ncu-rep --page raw --csv 2>/dev/null > profiles/${TAG}_observe_kernel_raw.csv
+python tools/ncu_mem_lines.py /tmp/${TAG}_src_step.csv > profiles/${TAG}_step_kernel_mem_lines.txt 2>/dev/null || true
+# SASS evidence: instruction mix per kernel of the shipped library (no tensor-core ops: there is no contraction on this path)
+{
+  echo "# cuobjdump -sass strikeforce_b200/libstrikeforce_b200.so: instructions per kernel and the mnemonics that matter"
+  cuobjdump -sass strikeforce_b200/libstrikeforce_b200.so | awk '
+    /Function : /{name=$3}
+    /^ +\/\*[0-9a-f]+\*\/ /{n[name]++; m=$2; if (m ~ /^@/) m=$3; sub(/\..*/,"",m); c[name" "m]++}
+    END{for(k in n) print n[k], k; for(k in c) print "  ", c[k], k}' | sort -k2,2 -k1,1nr | awk '$1=="" || $2 ~ /^(LDS|STS|LDG|STG|LDL|STL|BAR|REDUX|ATOMS|ATOMG|RED|SHFL|VOTE|HMMA|IMMA|UTCMMA|UBLKCP|UTMA|BSSY|CALL|IMAD|LOP3|ISETP)$/ || NF==2'
+} > profiles/${TAG}_sass_summary.txt
 python - <<PY
 import csv, json
 def dram(path):
@@ -32,10 +48,18 @@ def dram(path):
         i = hdr.index(k)
         return float(vals[i]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
     return b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
-json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture (tools/gpu_final.sh); bench.py copies them into roofline.traffic when it runs the same arena count",
-           "envs_per_gpu": 131072,
-           "sf_step_kernel": {"dram_bytes_per_launch": dram("profiles/${TAG}_step_kernel_raw.csv"), "source": "profiles/${TAG}_step_kernel_raw.csv"},
-           "sf_observe_kernel": {"dram_bytes_per_launch": dram("profiles/${TAG}_observe_kernel_raw.csv"), "source": "profiles/${TAG}_observe_kernel_raw.csv"}},
+bench = json.loads(open("profiles/${TAG}_bench.json").read().strip().splitlines()[-1])
+algo = bench["roofline"]["algo_bytes_per_launch"]
+step, obs = dram("profiles/${TAG}_step_kernel_raw.csv"), dram("profiles/${TAG}_observe_kernel_raw.csv")
+json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an ncu --set full capture taken inside the timed region of the "
+                   "bench command itself (tools/gpu_final.sh), next to the algorithmic bytes of a launch of that same region; bench.py copies "
+                   "dram_bytes_per_launch into roofline.traffic when it runs the same arena count",
+           "envs_per_gpu": bench["config"]["envs_per_gpu"],
+           "sf_step_kernel": {"dram_bytes_per_launch": step, "algo_bytes_per_launch": algo, "traffic_over_algorithmic": step / algo,
+                              "source": "profiles/${TAG}_step_kernel_raw.csv"},
+           "sf_observe_kernel": {"dram_bytes_per_launch": obs, "algo_bytes_per_launch": bench["config"]["envs_per_gpu"] * 123008,
+                                 "traffic_over_algorithmic": obs / (bench["config"]["envs_per_gpu"] * 123008),
+                                 "source": "profiles/${TAG}_observe_kernel_raw.csv"}},
           open("profiles/traffic.json", "w"), indent=1)
 PY
 echo collected

@@ -239,6 +239,7 @@ __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfCo
 #define SF_OBS_GROUP (SF_OBS_CELLS)  /* chunks per 4-channel group: 4 * 961 floats / 4 */
 #define SF_OBS_SMEM (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 4 * SF_OBS_LIST * 2 + 16)
 static_assert(SF_OBS_CELLS % 4 == 1 && SF_OBS_CH % 4 == 0, "the copy-out relies on 4 channels = 961 whole chunks");
+static_assert(SF_OBS_ROWS % 4 == 0, "the arrays behind the table stay 16-byte aligned");
 
 /* (arena, observed human slot) of work item `item` */
 __device__ __forceinline__ void sf_obs_item(int item, int nsel, uint32_t agent_mask, int *env, int *slot)
@@ -351,8 +352,9 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         }
         __syncthreads();
         /* the copy-out: no barrier, no shared-memory buffer between the table and HBM; every store
-           instruction of a warp covers 512 contiguous bytes (storing the all-zero chunks first and the
-           others in a second pass, lane-dense, was measured 40% SLOWER: partial-warp stores) */
+           instruction of a warp covers 512 contiguous bytes.  Measured and rejected: storing the all-zero
+           chunks first and the others in a second pass, lane-dense (41% slower: partial-warp stores); a
+           warp vote that sends 128 empty cells in a row down a store-only path (7% slower) */
         float4 *dst = reinterpret_cast<float4 *>(out);
         for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
             int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */

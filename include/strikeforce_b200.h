@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 2
+#define SF_ABI_VERSION 3
 
 /* arena geometry of the reference (gameplay.hpp:37: F = 3, N = 30, M = 100) */
 #define SF_FLOORS 3
@@ -87,13 +87,19 @@ typedef struct sf_config {
        gameplay.hpp:1795-1859): humans 0 .. royale_players-1 are players, every one of them with
        a sheet and a command of their own each step (sf_step: actions[env][player], any
        symbol of the alphabet); player i belongs to team royale_teams[i] (1..7); arena slot 0 is
-       `ind`, the player whose death or victory ends the match: it carries player_sheet (hum[ind] =
-       me), player i > 0 the sheet royale_sheets[i] it announced (get_info / scan_file,
+       `ind` unless royale_ind says otherwise, the player whose death or victory ends the match: it carries
+       player_sheet (hum[ind] = me), every other player i the sheet royale_sheets[i] it announced (get_info / scan_file,
        gameplay.hpp:131-149, 1797-1806).  Each player gets way = rand()%4+1 and a rejection-sampled
        '.' cell; the level is 1 (gameplay.hpp:1641, 1659). */
     int32_t royale_players;          /* 2..SF_MAX_PLAYERS */
     int32_t royale_teams[SF_MAX_PLAYERS];
-    int32_t royale_sheets[SF_MAX_PLAYERS][SF_SHEET_LEN]; /* row 0 is not read */
+    int32_t royale_sheets[SF_MAX_PLAYERS][SF_SHEET_LEN]; /* row royale_ind is not read */
+    /* which player of a Battle Royale arena is `ind`, the player whose copy of the match this is
+       (0 .. royale_players-1; 0 elsewhere): kill and loot credits go to `ind` and its team
+       (gameplay.hpp:591-592, 629-630), its corpse keeps its cell (:642-645), its death or its team's
+       victory ends the match, sf_step_out reports its Hp / damage / effect.  Every client of an online
+       match holds such a copy; a match server that keeps one arena per seat sets this per handle. */
+    int32_t royale_ind;
 } sf_config;
 
 typedef struct sf_handle sf_handle;

@@ -65,6 +65,7 @@ struct sfo_arena {
     int mode, squad_agents, max_steps;
     int n_players, teams[SF_MAX_PLAYERS]; /* SF_MODE_ROYALE: `players` and the teams of the replay header */
     int32_t royale_sheets[SF_MAX_PLAYERS][SF_SHEET_LEN]; /* the sheets the other players announced */
+    int royale_ind;                                       /* which player is `ind` in a Battle Royale match */
     int cap_h, cap_z, cap_b, cap_chest, cap_built, cap_portal;
     uint8_t map_cells[SF_CELLS];
     int16_t map_portal[SF_CELLS];
@@ -862,13 +863,14 @@ static void setup(sfo_arena *a)
                     a->active[index] = 1;
                 }
             }
-    a->ind = 0;
+    const int me = a->mode == SF_MODE_ROYALE ? a->royale_ind : 0; /* "players ind team" of the match header, :1797-1799 */
+    a->ind = me;
     memset(a->remote, 0, sizeof a->remote);
-    a->mh[0] = 1;
-    memset(&a->hum[0], 0, sizeof a->hum[0]);
-    human_build(&a->hum[0], a->player_sheet, 0); /* hum[ind] = me, me.build(false, "", sheet) */
-    a->hum[0].way = 1;
-    a->hum[0].team = 1;
+    a->mh[me] = 1;
+    memset(&a->hum[me], 0, sizeof a->hum[me]);
+    human_build(&a->hum[me], a->player_sheet, 0); /* hum[ind] = me, me.build(false, "", sheet) */
+    a->hum[me].way = 1;
+    a->hum[me].team = 1;
     if (a->mode == SF_MODE_SQUAD) {
         a->hum[0].cor[0] = 0, a->hum[0].cor[1] = 3, a->hum[0].cor[2] = 1;
         a->themap[0][3][1].human = 0, a->themap[0][3][1].s[0] = 1;
@@ -890,8 +892,9 @@ static void setup(sfo_arena *a)
         /* load_data(), online branch as the replay reader runs it (:1776-1806): every player's
            sheet comes from the match header.  The cells are drawn after the stream is seeded
            (place_players) */
-        a->hum[0].team = a->teams[0];
-        for (int i = 1; i < a->n_players; ++i) {
+        a->hum[me].team = a->teams[me];
+        for (int i = 0; i < a->n_players; ++i) {
+            if (i == me) continue;
             memset(&a->hum[i], 0, sizeof a->hum[i]);
             human_build(&a->hum[i], a->royale_sheets[i], 0);
             a->hum[i].team = a->teams[i];
@@ -903,7 +906,7 @@ static void setup(sfo_arena *a)
         a->hum[0].cor[0] = 0, a->hum[0].cor[1] = 1, a->hum[0].cor[2] = 1;
         a->themap[0][1][1].human = 0, a->themap[0][1][1].s[0] = 1;
     }
-    a->hum[0].agent_active = 1; /* prepare(me), :1743-1744 */
+    a->hum[me].agent_active = 1; /* prepare(me), :1743-1744 */
 }
 
 /* gameplay.hpp:1847-1859: way and a rejection-sampled '.' cell for every player, in index order */
@@ -992,6 +995,8 @@ sfo_arena *sfo_create(const sf_config *cfg)
         a->n_players = cfg->royale_players;
         for (int i = 0; i < a->n_players; ++i) a->teams[i] = cfg->royale_teams[i];
         memcpy(a->royale_sheets, cfg->royale_sheets, sizeof a->royale_sheets);
+        if (cfg->royale_ind < 0 || cfg->royale_ind >= a->n_players) return free(a), (sfo_arena *)NULL;
+        a->royale_ind = cfg->royale_ind;
     }
     a->squad_agents = cfg->squad_agents != 0;
     a->max_steps = cfg->max_steps;
@@ -1075,7 +1080,7 @@ static int step_a_(sfo_arena *a)
 /* second half, gameplay.hpp:1462-1471, then the harness's end-of-step victory test */
 static int step_b_(sfo_arena *a, const uint8_t *actions, int n)
 {
-    a->command[a->ind] = n > 0 ? actions[0] : '+';
+    a->command[a->ind] = n > a->ind ? actions[a->ind] : '+'; /* actions[] is indexed by human slot */
     uint8_t cmd[64];
     int nc = n < 64 ? n : 64;
     for (int i = 0; i < nc; ++i) { /* harness action_index(): symbols outside gameplay::action read '+' */

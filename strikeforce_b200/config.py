@@ -14,7 +14,7 @@ import numpy as np
 
 from . import data as sfdata
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLOORS, ROWS, COLS = 3, 30, 100  # SF_FLOORS / SF_ROWS / SF_COLS (gameplay.hpp:37)
 CELLS = FLOORS * ROWS * COLS
 OBS_CH, OBS_WIN = 32, 31
@@ -77,6 +77,7 @@ class SfConfig(C.Structure):
         ("royale_players", C.c_int32),
         ("royale_teams", C.c_int32 * MAX_PLAYERS),
         ("royale_sheets", (C.c_int32 * SHEET_LEN) * MAX_PLAYERS),
+        ("royale_ind", C.c_int32),
     ]
 
 
@@ -91,11 +92,12 @@ DEFAULT_CAPS = dict(cap_humans=64, cap_zombies=128, cap_bullets=96, cap_chests=9
 
 
 def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, level_max=None, squad_agents=False,
-                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None, teams=None, sheets=None):
+                auto_reset=True, max_steps=0, env_id_base=0, player="account1", caps=None, teams=None, sheets=None, ind=0):
     """Build an ``sf_config``.  The returned struct keeps the numpy arrays it points to alive
     (``cfg._keep``).  Battle Royale only: ``teams`` = the team of each player, e.g. ``[1, 1, 2, 2]``;
     ``sheets`` = the character sheet of each player (names or int32[32] arrays; default: every
-    player carries ``player``; entry 0 is the sheet of ``ind`` and replaces ``player``)."""
+    player carries ``player``; entry ``ind`` is the sheet of ``ind`` and replaces ``player``); ``ind`` = the
+    player whose copy of the match the arenas are (credits, the corpse that keeps its cell, the end of the match)."""
     if isinstance(mode, str):
         mode = MODES[mode]
     cfg = SfConfig()
@@ -125,7 +127,7 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
         return arena.player_sheet(x) if isinstance(x, str) else np.asarray(x, dtype=np.int32)
 
     if mode == MODE_ROYALE and sheets is not None:
-        player = sheets[0]
+        player = sheets[ind]
     sheet = as_sheet(player)
     for i in range(SHEET_LEN):
         cfg.player_sheet[i] = int(sheet[i])
@@ -142,6 +144,9 @@ def make_config(arena: sfdata.ArenaData, n_envs=1, mode=MODE_SOLO, level_min=1, 
             sh = sheet if sheets is None else as_sheet(sheets[i])
             for j in range(SHEET_LEN):
                 cfg.royale_sheets[i][j] = int(sh[j])
+        if not 0 <= ind < len(teams):
+            raise ValueError("ind must name one of the players")
+        cfg.royale_ind = ind
         cfg.level_min = cfg.level_max = 1  # gameplay.hpp:1641, 1659
     cfg._keep = (cells, portal)
     return cfg

@@ -62,7 +62,7 @@ SF_FN void sf_canon_emit(const SfDev &d, const SfConst &k, const SfTabs &t, int 
     sf_load_env(d, env, e);
     int32_t f[32];
     f[0] = k.mode, f[1] = e.level, f[2] = (int32_t)e.frame, f[3] = e.kills, f[4] = e.tkills, f[5] = e.loot;
-    f[6] = e.chest, f[7] = 0;
+    f[6] = e.chest, f[7] = k.ind;
     sink.elem(SF_K_HEADER, 0, f, SF_NF_HEADER);
     for (int i = 0; i < 18; ++i) f[i] = (int32_t)sf_exp_m1(t, 2u * sf_rng_log(e, i)) + 1;
     f[18] = (int32_t)(e.jomle & 0xFFFFu);

@@ -904,7 +904,8 @@ SF_FN void sf_check_built(const SfDev &d, const SfConst &k, int env, SfEnv &e, i
 }
 
 /* human_damage, gameplay.hpp:611-634 */
-SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int cell, uint32_t g, uint32_t meta)
+SF_FN void sf_human_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e, int h, int b, int cell, uint32_t g,
+                           uint32_t meta)
 {
     int dmg = SF_AT(d.b_dmg, b), eff = SF_AT(d.b_eff, b);
     int owner = (int)((meta >> 16) & 0xFFu) - 1;
@@ -914,27 +915,28 @@ SF_FN void sf_human_damage(const SfDev &d, int env, SfEnv &e, int h, int b, int 
     m2_clear(e.mb, b); /* with its owner the cell's bullet flag is gone */
     uint32_t team_h = SF_AT(d.h_sel, h) & HS_TEAM;
     uint32_t team_o = owner >= 0 ? (SF_AT(d.h_sel, owner) & HS_TEAM) : 0u;
-    uint32_t team_me = SF_AT(d.h_sel, 0) & HS_TEAM;
+    uint32_t team_me = SF_AT(d.h_sel, k.ind) & HS_TEAM;
     if (owner >= 0 && team_h != team_o) {
         SF_AT(d.h_dmg, owner) += dmg;
         SF_AT(d.h_eff, owner) += eff;
     }
     if (hp <= 0) {
         e.mh &= ~(1ull << h);
-        if (h != 0) {
+        if (h != k.ind) { /* the own corpse keeps its cell, gameplay.hpp:642-645 */
             SF_G(cell) = (uint16_t)(g & ~(C_S0 | C_OCC));
             SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT); /* deleteAgent, :648-649 */
         }
         if (owner >= 0 && team_o == team_me && team_h != team_me) {
             e.tkills += 1, e.loot += 100;
-            if (owner == 0) e.loot += 900, e.kills += 1;
+            if (owner == k.ind) e.loot += 900, e.kills += 1;
         }
         if (owner >= 0 && team_h != team_o) SF_AT(d.h_kills, owner) += 1;
     }
 }
 
 /* zombie_damage, gameplay.hpp:574-598 */
-SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int cell, uint32_t g, uint32_t meta)
+SF_FN void sf_zombie_damage(const SfDev &d, const SfConst &k, int env, SfEnv &e, int z, int b, int cell, uint32_t g,
+                            uint32_t meta)
 {
     int dmg = SF_AT(d.b_dmg, b), eff = SF_AT(d.b_eff, b);
     int owner = (int)((meta >> 16) & 0xFFu) - 1;
@@ -949,10 +951,10 @@ SF_FN void sf_zombie_damage(const SfDev &d, int env, SfEnv &e, int z, int b, int
     if (hp <= 0) {
         m2_clear(e.mz, z);
         SF_G(cell) = (uint16_t)(g & ~(C_S1 | C_OCC));
-        if (owner >= 0 && (SF_AT(d.h_sel, owner) & HS_TEAM) == (SF_AT(d.h_sel, 0) & HS_TEAM)) {
+        if (owner >= 0 && (SF_AT(d.h_sel, owner) & HS_TEAM) == (SF_AT(d.h_sel, k.ind) & HS_TEAM)) {
             int pts = 500 + 250 * (int)(SF_AT(d.z_pos, z) >> POS_HI_SHIFT);
             e.tkills += 1, e.loot += pts / 10;
-            if (owner == 0) e.loot += pts * 9 / 10, e.kills += 1;
+            if (owner == k.ind) e.loot += pts * 9 / 10, e.kills += 1;
         }
         if (owner >= 0) SF_AT(d.h_kills, owner) += 1;
     }
@@ -1043,9 +1045,9 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, const SfTabs &t,
                 } else if (mj & BF_OWNS) {
                     int occ = (int)(gj & C_OCC);
                     if ((gj & C_S0) && ((e.mh >> occ) & 1) && !((quitters >> occ) & 1)) {
-                        sf_human_damage(d, env, e, occ, b, cj, gj, mj);
+                        sf_human_damage(d, k, env, e, occ, b, cj, gj, mj);
                     } else if (gj & C_S1) {
-                        sf_zombie_damage(d, env, e, occ, b, cj, gj, mj);
+                        sf_zombie_damage(d, k, env, e, occ, b, cj, gj, mj);
                     }
                 }
             }
@@ -1071,7 +1073,7 @@ SF_FN void sf_resolve_bullets(const SfDev &d, const SfConst &k, const SfTabs &t,
             int h = sf_ffs64(q);
             q &= q - 1;
             e.mh &= ~(1ull << h);
-            if (h != 0) {
+            if (h != k.ind) {
                 int cell = (int)(SF_AT(d.h_pw, h) & POS_CELL);
                 SF_G(cell) = (uint16_t)(SF_G(cell) & ~(C_S0 | C_OCC));
                 SF_AT(d.h_sel, h) = (uint16_t)(SF_AT(d.h_sel, h) & ~HS_AGENT);
@@ -1397,16 +1399,19 @@ SF_FN void sf_obey(const SfDev &d, const SfConst &k, const SfTabs &t, int env, S
 }
 
 /* human_action, gameplay.hpp:965-1012.  actions = this arena's row of the action buffer:
- * [0] the player's command (get_my_action, :939-963), [1..] what bot() returns for the
- * agent-driven squad humans (bots/bot-0.5/Custom.hpp:137-158, one of "+xzqeawsd"). */
+ * [ind] the player's command (get_my_action, :939-963; ind = 0 outside Battle Royale), the other
+ * entries what bot() returns for the agent-driven squad humans (bots/bot-0.5/Custom.hpp:137-158, one
+ * of "+xzqeawsd") or, in Battle Royale, what the other players sent. */
 SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, int env, SfEnv &e,
                            const uint8_t *actions)
 {
     /* commands wait in h_cmd between the two loops (command[], gameplay.hpp:43) */
     const uint64_t live = e.on ? e.mh : 0ull;
     const int hi = SF_WARP_MAX(live ? sf_fls64(live) : -1);
-    const int cmd0 = (actions && e.on) ? actions[0] : '+';
-    for (int h = 1; h <= hi; ++h) {
+    const int ind = k.ind;
+    const int cmd0 = (actions && e.on) ? actions[ind] : '+';
+    for (int h = 0; h <= hi; ++h) {
+        if (h == ind) continue; /* command[ind] is the player's own, set before human_action (:956-961) */
         bool is_live = (live >> h) & 1;
         uint32_t sel = is_live ? SF_AT(d.h_sel, h) : 0u;
         int c = sf_rnpc_bot(t, e, is_live && (sel & HS_RNPC));
@@ -1433,7 +1438,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
     {
         int h = r ? 0 : hi;
         if (hi >= 0 && ((live >> h) & 1))
-            pw_n = SF_AT(d.h_pw, h), sel_n = SF_AT(d.h_sel, h), c_n = h == 0 ? cmd0 : (int)SF_AT(d.h_cmd, h);
+            pw_n = SF_AT(d.h_pw, h), sel_n = SF_AT(d.h_sel, h), c_n = h == ind ? cmd0 : (int)SF_AT(d.h_cmd, h);
     }
     for (int i = 0; i <= hi; ++i) {
         const int h = r ? i : hi - i;
@@ -1442,7 +1447,7 @@ SF_FN void sf_human_action(const SfDev &d, const SfConst &k, const SfTabs &t, in
         if (i < hi) {
             int hn = r ? i + 1 : hi - i - 1;
             if ((live >> hn) & 1)
-                pw_n = SF_AT(d.h_pw, hn), sel_n = SF_AT(d.h_sel, hn), c_n = hn == 0 ? cmd0 : (int)SF_AT(d.h_cmd, hn);
+                pw_n = SF_AT(d.h_pw, hn), sel_n = SF_AT(d.h_sel, hn), c_n = hn == ind ? cmd0 : (int)SF_AT(d.h_cmd, hn);
         }
         if (e.on && ((live >> h) & 1)) sf_obey(d, k, t, env, e, h, c, pw, sel);
         SF_SYNCWARP();
@@ -1542,7 +1547,7 @@ SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
     if (e.on) {
         bool rivals = false; /* rivals_are_dead, gameplay.hpp:497-505 */
         if (k.mode == SF_MODE_ROYALE) {
-            uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
+            uint32_t me = SF_AT(d.h_sel, k.ind) & HS_TEAM;
             for (uint64_t m = e.mh; m; m &= m - 1) {
                 uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
                 if (tm && tm != me) rivals = true;
@@ -1550,7 +1555,7 @@ SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
         }
         if (k.mode == SF_MODE_ROYALE && !rivals) {
             e.status = SF_WIN; /* "online && rivals_are_dead()" is the first test of check_end(), :1103 */
-        } else if (SF_AT(d.h_hp, 0) <= 0) {
+        } else if (SF_AT(d.h_hp, k.ind) <= 0) {
             e.status = SF_DEAD;
         } else if (k.mode == SF_MODE_ROYALE) {
             /* an online match ends in no other way */
@@ -1560,7 +1565,7 @@ SF_FN void sf_eval_end(const SfDev &d, const SfConst &k, int env, SfEnv &e)
             if (e.level * 5 <= e.kills) e.status = SF_WIN;
         } else if (e.level * 10 <= e.tkills) {
             /* rivals_are_dead, gameplay.hpp:497-505 */
-            uint32_t me = SF_AT(d.h_sel, 0) & HS_TEAM;
+            uint32_t me = SF_AT(d.h_sel, k.ind) & HS_TEAM;
             bool alive = false;
             for (uint64_t m = e.mh; m; m &= m - 1) {
                 uint32_t tm = SF_AT(d.h_sel, sf_ffs64(m)) & HS_TEAM;
@@ -1710,7 +1715,7 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         if (half == SF_HALF_B) o = d.out[env];
         else o.status = 0, o.d_kills = o.d_teams_kills = o.d_loot = o.d_hp = o.d_damage = o.d_effect = 0, o.episode_steps = 0;
         o.d_kills -= e.kills, o.d_teams_kills -= e.tkills, o.d_loot -= e.loot;
-        o.d_hp -= SF_AT(d.h_hp, 0), o.d_damage -= SF_AT(d.h_dmg, 0), o.d_effect -= SF_AT(d.h_eff, 0);
+        o.d_hp -= SF_AT(d.h_hp, k.ind), o.d_damage -= SF_AT(d.h_dmg, k.ind), o.d_effect -= SF_AT(d.h_eff, k.ind);
         d.out[env] = o;
     }
     if (half != SF_HALF_B && e.on) sd.algo_bytes += sf_algo_bytes(k, e);
@@ -1720,7 +1725,7 @@ SF_FN void sf_step_body(const SfDev &d, const SfConst &k, const SfTabs &t, int e
         /* a terminal arena that is not auto-reset waits for sf_reset: report, change nothing */
         sf_step_out o = d.out[env];
         o.d_kills += e.kills, o.d_teams_kills += e.tkills, o.d_loot += e.loot;
-        o.d_hp += SF_AT(d.h_hp, 0), o.d_damage += SF_AT(d.h_dmg, 0), o.d_effect += SF_AT(d.h_eff, 0);
+        o.d_hp += SF_AT(d.h_hp, k.ind), o.d_damage += SF_AT(d.h_dmg, k.ind), o.d_effect += SF_AT(d.h_eff, k.ind);
         o.status = e.status;
         o.episode_steps = (int32_t)e.steps;
         d.out[env] = o;

@@ -129,6 +129,9 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
         if (cfg.level_min != 1 || cfg.level_max != 1) return "Battle Royale is played at level 1 (gameplay.hpp:1641)";
         for (int i = 0; i < cfg.royale_players; ++i)
             if (cfg.royale_teams[i] < 1 || cfg.royale_teams[i] > 7) return "royale_teams must be 1..7";
+        if (cfg.royale_ind < 0 || cfg.royale_ind >= cfg.royale_players) return "royale_ind must name one of the players";
+    } else if (cfg.royale_ind != 0) {
+        return "royale_ind is a Battle Royale setting";
     }
     if (!cfg.map_cells || !cfg.map_portal) return "map_cells / map_portal missing";
     if (cfg.level_min < 1 || cfg.level_max < cfg.level_min || cfg.level_max > SF_MAX_LEVEL) return "level range";
@@ -143,6 +146,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     k.mode = cfg.mode, k.squad_agents = cfg.squad_agents != 0, k.auto_reset = cfg.auto_reset != 0;
     k.max_steps = cfg.max_steps, k.level_min = cfg.level_min, k.level_span = cfg.level_max - cfg.level_min + 1;
     k.n_players = cfg.mode == SF_MODE_ROYALE ? cfg.royale_players : 1;
+    k.ind = cfg.mode == SF_MODE_ROYALE ? cfg.royale_ind : 0;
     k.n_agents = cfg.mode == SF_MODE_ROYALE ? k.n_players : (cfg.mode == SF_MODE_SQUAD && cfg.squad_agents) ? 10 : 1;
     for (int i = 0; i < k.n_players && cfg.mode == SF_MODE_ROYALE; ++i) k.teams[i] = (uint8_t)cfg.royale_teams[i];
     k.cap_h = cfg.cap_humans, k.cap_z = cfg.cap_zombies, k.cap_b = cfg.cap_bullets, k.cap_chest = cfg.cap_chests;
@@ -198,7 +202,7 @@ inline std::string build_const(const sf_config &cfg, SfConst &k, Tables &t)
     };
     if (const char *e = sheet_error(cfg.npc_sheet)) return e;
     for (int p = 0; p < k.n_players; ++p) {
-        const int32_t *sh = p == 0 ? cfg.player_sheet : cfg.royale_sheets[p];
+        const int32_t *sh = p == k.ind ? cfg.player_sheet : cfg.royale_sheets[p]; /* hum[ind] = me */
         if (const char *e = sheet_error(sh)) return e;
         build_template(k.players[p], sh, cfg);
         if (k.players[p].blocks > 255 || k.players[p].portals > 255) return "block / portal allowance above 255";

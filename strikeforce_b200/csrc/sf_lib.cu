@@ -179,14 +179,14 @@ __global__ void sf_export_kernel(const SfDev d, const __grid_constant__ SfConst 
     *n_out = sink.overflow ? -1 : sink.n;
 }
 
-__global__ void sf_counters_kernel(const SfDev d, int32_t *out)
+__global__ void sf_counters_kernel(const SfDev d, const __grid_constant__ SfConst k, int32_t *out)
 {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n_envs) return;
     uint32_t misc = d.misc[env];
     int32_t *o = out + (size_t)env * 8;
     o[0] = (int32_t)d.frame[env], o[1] = d.kills[env], o[2] = d.tkills[env], o[3] = d.loot[env];
-    o[4] = d.chest[env], o[5] = (int32_t)d.steps[env], o[6] = (int32_t)((misc >> 8) & 0xFFu), o[7] = SF_AT(d.h_hp, 0);
+    o[4] = d.chest[env], o[5] = (int32_t)d.steps[env], o[6] = (int32_t)((misc >> 8) & 0xFFu), o[7] = SF_AT(d.h_hp, k.ind);
 }
 
 __global__ void sf_population_kernel(const SfDev d, const __grid_constant__ SfConst k, int32_t *out)
@@ -808,7 +808,7 @@ int sf_get(sf_handle *h, int32_t field, void *dev_out, void *stream)
         sf_hash_kernel<<<grid, 128, 0, s>>>(h->d, h->k, static_cast<uint64_t *>(dev_out));
         break;
     case SF_FIELD_COUNTERS:
-        sf_counters_kernel<<<grid, 128, 0, s>>>(h->d, static_cast<int32_t *>(dev_out));
+        sf_counters_kernel<<<grid, 128, 0, s>>>(h->d, h->k, static_cast<int32_t *>(dev_out));
         break;
     case SF_FIELD_POPULATION:
         sf_population_kernel<<<grid, 128, 0, s>>>(h->d, h->k, static_cast<int32_t *>(dev_out));

@@ -127,13 +127,14 @@ typedef struct SfTemplate {
 typedef struct SfConst {
     int32_t mode, squad_agents, auto_reset, max_steps, level_min, level_span, n_agents;
     int32_t n_players;                      /* humans 0 .. n_players-1 carry the player sheet (1 except in Battle Royale) */
+    int32_t ind;                            /* `ind`: the player whose copy of the match this is (0 except in Battle Royale) */
     uint8_t teams[SF_MAX_PLAYERS];          /* Battle Royale: team of each player */
     int32_t cap_h, cap_z, cap_b, cap_chest, cap_t, cap_p;
     int64_t env_id_base;
     int32_t n_static_exits;
     uint16_t static_exit_cell[SF_MAX_STATIC_EXITS];
     sf_consumable cons[4];
-    SfTemplate players[SF_MAX_PLAYERS], npc; /* [0] = `me`; [1..] only in Battle Royale */
+    SfTemplate players[SF_MAX_PLAYERS], npc; /* [ind] = `me`; the others only in Battle Royale */
     int32_t player_punch_base[SF_MAX_PLAYERS]; /* compute_damage(mindamage_def, 1), Character.hpp:393 */
     int32_t npc_punch_base[SF_MAX_LEVEL + 1]; /* per level: gen_human's level-ups, :883-887 */
     int32_t npc_mindamage_def[SF_MAX_LEVEL + 1];

@@ -21,7 +21,8 @@ from .lib import check, lib
 
 class BatchedArena:
     def __init__(self, n_envs, mode="Solo", level=1, level_max=None, squad_agents=False, auto_reset=True,
-                 max_steps=0, env_id_base=0, player="account1", caps=None, arena=None, device=None, teams=None, sheets=None):
+                 max_steps=0, env_id_base=0, player="account1", caps=None, arena=None, device=None, teams=None, sheets=None,
+                 ind=0):
         if not torch.cuda.is_available():
             # fail loudly: there is no CPU path (sf_create would report SF_ERR_NO_DEVICE as well)
             raise RuntimeError("strikeforce_b200 needs a CUDA device; it has no CPU fallback")
@@ -30,7 +31,7 @@ class BatchedArena:
         self.arena = arena or sfdata.load_default()
         self.cfg = sfcfg.make_config(self.arena, n_envs=n_envs, mode=mode, level_min=level, level_max=level_max,
                                      squad_agents=squad_agents, auto_reset=auto_reset, max_steps=max_steps,
-                                     env_id_base=env_id_base, player=player, caps=caps, teams=teams, sheets=sheets)
+                                     env_id_base=env_id_base, player=player, caps=caps, teams=teams, sheets=sheets, ind=ind)
         self._h = C.c_void_p()
         check(lib().sf_create(C.byref(self.cfg), C.byref(self._h)))
         self.n_envs = n_envs

@@ -59,6 +59,8 @@ def golden_kwargs(g):
         kw["caps"] = dict(zip(CAP_KEYS, (int(c) for c in g["caps"])))
         if "sheets" in g:
             kw["sheets"] = [str(n) for n in g["sheets"]]
+        if "ind" in g:
+            kw["ind"] = int(g["ind"])
     return kw
 
 

@@ -39,6 +39,11 @@ CASES = [
     # every player with a sheet of its own, as announced over the wire (get_info, gameplay.hpp:131-149)
     ("royale_6p_mixed_sheets", [1, 2, 3, 1, 2, 3], 1700000003, 3003, 3000,
      ["account1", "new_player", "synthetic", "new_player", "account1", "synthetic"]),
+    # the copy of a match that belongs to a player other than 0 ("players ind team" of the header,
+    # gameplay.hpp:1797-1799): credits, the corpse that keeps its cell and the end of the match follow `ind`
+    ("royale_5p_ind2", [1, 2, 1, 3, 2], 1700000055, 55055, 3000,
+     ["new_player", "account1", "account1", "synthetic", "new_player"], 2),
+    ("royale_4p_ind3_short", [1, 2, 2, 1], 1700000009, 9009, 8000, "new_player", 3),
 ]
 
 
@@ -46,14 +51,16 @@ def main(which):
     """One match per process: the reference keeps its humans in globals, and a slot that held a
     player of team 3 in the match before would hand that team to the NPC spawned into it."""
     arena = sfdata.load_default()
-    for name, teams, tb, serial, steps, player in [CASES[which]]:
+    for case in [CASES[which]]:
+        name, teams, tb, serial, steps, player = case[:6]
+        ind = case[6] if len(case) > 6 else 0
         names = player if isinstance(player, list) else [player] * len(teams)
         sheet = np.stack([arena.player_sheet(n) for n in names])
         P = len(teams)
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         table = np.frombuffer(bytes(sfcfg.ACTIONS28), dtype=np.uint8)
         actions = table[rng.integers(len(table), size=(steps, P))]
-        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS, sheets=names)
+        cfg = sfcfg.make_config(arena, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, caps=CAPS, sheets=names, ind=ind)
         o = sfo.Arena(cfg)
         o.reset(1, tb, serial)
         file_cmds = bytearray()
@@ -62,13 +69,13 @@ def main(which):
             if o.step_a() != 0:
                 break
             rec = sfo.parse_record(o.dump())
-            file_cmds.append(actions[t, 0])
-            file_cmds.extend(actions[t, i] for i in range(1, P) if rec[(3, i)][0])
+            file_cmds.append(actions[t, ind])
+            file_cmds.extend(actions[t, i] for i in range(P) if i != ind and rec[(3, i)][0])
             n = t + 1
             if o.step_b(bytes(actions[t])) != 0:
                 break
         path = os.path.join(tempfile.mkdtemp(), name + ".sf_sample")
-        replay.write_royale(path, tb, serial, sheet, teams, bytes(file_cmds))
+        replay.write_royale(path, tb, serial, sheet, teams, bytes(file_cmds), ind=ind)
         sfref.reset_replay(sfcfg.MODE_ROYALE, 1, path, caps=[CAPS[k] for k in CAP_KEYS])
         status = np.zeros(n, dtype=np.int32)
         hashes = np.zeros(n + 1, dtype=np.uint64)
@@ -76,7 +83,10 @@ def main(which):
         obs, obs_steps, obs_last, records, rec_steps = [], [], [], [], []
         for t in range(n):
             if t % 100 == 0:
-                obs.append(sfref.observe(0))
+                try:
+                    obs.append(sfref.observe(0))
+                except RuntimeError:  # player 0 is a remote player here (ind != 0) and has died
+                    obs.append(np.full(sfref.OBS_LEN, np.nan, dtype=np.float32))
                 try:
                     obs_last.append(sfref.observe(P - 1))
                 except RuntimeError:  # that player is dead: its agent is gone
@@ -93,7 +103,8 @@ def main(which):
         actions = actions[:len(status)]
         assert o.status() == status[-1] and np.uint64(o.state_hash()) == hashes[-1] or status[-1] in (5, 6)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), mode=sfcfg.MODE_ROYALE, level=1, tb=tb, serial=serial,
-                            squad_agents=0, player=names[0], sheets=np.array(names), teams=np.array(teams), caps=np.array([CAPS[k] for k in CAP_KEYS]),
+                            squad_agents=0, player=names[ind], sheets=np.array(names), teams=np.array(teams), ind=ind,
+                            caps=np.array([CAPS[k] for k in CAP_KEYS]),
                             actions=actions, status=status, hashes=hashes, records=np.concatenate(records),
                             rec_len=np.array([len(r) for r in records], dtype=np.int64), rec_steps=np.array(rec_steps),
                             obs=np.stack(obs), obs_last=np.stack(obs_last), obs_steps=np.array(obs_steps),

@@ -177,15 +177,20 @@ def _hosted_match_with_reference_clients(arena_data, table, T):
         host.handshake()
         account = "\n".join(l.strip() for l in open(sfref.ACCOUNT1).read().strip().splitlines())
         assert all("\n".join(l.strip() for l in s.strip().splitlines()) == account for s in host.sheets.values())
-        cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False)
-        arena = sfo.Arena(cfg)
-        arena.reset(1, tb, serial)
-        mine = []
+        # one arena PER SEAT: the copy of the match that belongs to seat s (sf_config.royale_ind = s) -- what
+        # that seat's own client computes, credits and corpse included
+        arenas = []
+        for s in range(len(teams)):
+            a = sfo.Arena(sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, ind=s))
+            a.reset(1, tb, serial)
+            arenas.append(a)
+        mine = [[] for _ in teams]
 
         def step(row):
-            if arena.status() == 0:
-                st = arena.step(row)
-                mine.append((st,) + common.record_crcs(arena.dump()))
+            for s, a in enumerate(arenas):
+                if a.status() == 0:
+                    st = a.step(row)
+                    mine[s].append((st,) + common.record_crcs(a.dump()))
 
         winner, ticks = ms.host_match(host, step, max_ticks=T)
         results = {}
@@ -263,22 +268,23 @@ def test_reference_clients_join_a_hosted_match(arena_data):
     ind-specific rules (kill credits, the own corpse) out of play."""
     T = 400
     mine, results, winner, ticks = _hosted_match_with_reference_clients(arena_data, common.MATCH_TABLE, T)
-    assert ticks == T and winner == 0 and len(mine) == T
+    assert ticks == T and winner == 0 and all(len(m) == T for m in mine)
     for ind, theirs in results.items():
         assert len(theirs) == T
-        bad = [t for t in range(T) if theirs[t][:2] != mine[t][:2]]
-        assert not bad, "client %d and the host part at tick %d" % (ind, bad[0])
+        bad = [t for t in range(T) if theirs[t][:2] != mine[ind][t][:2]]
+        assert not bad, "client %d and the host's arena of that seat part at tick %d" % (ind, bad[0])
 
 
 def test_reference_clients_fight_in_a_hosted_match(arena_data):
-    """The same with the whole alphabet (shots, throwables, blocks, portals): the client that holds
-    seat 0 -- the seat whose copy the host's arena is -- must match it completely; the other client's
-    copy may differ in what depends on `ind` (header counters, cells) and must match in everything
-    else: RNG state, every human, zombie, bullet and portal."""
+    """The same with the whole alphabet (shots, throwables, blocks, portals), where the rules that depend
+    on whose copy a match is come into play (kill and loot credits, the own corpse keeping its cell,
+    gameplay.hpp:591-592, 629-630, 642-645): the host keeps one arena per seat (royale_ind = seat) and EVERY
+    client's copy must equal the host's arena of its seat completely, tick by tick, until that copy ends."""
     T = 1500
     mine, results, winner, ticks = _hosted_match_with_reference_clients(arena_data, sfcfg.ACTIONS28, T)
-    n = min(len(mine), min(len(r) for r in results.values()))
-    assert n >= 200
-    for t in range(n):
-        assert results[0][t][:2] == mine[t][:2], "seat 0's client and the host part at tick %d" % t
-        assert results[1][t][2] == mine[t][2], "seat 1's client and the host part at tick %d" % t
+    for ind, theirs in results.items():
+        n = min(len(mine[ind]), len(theirs))
+        assert n >= 200
+        for t in range(n):
+            assert theirs[t][:2] == mine[ind][t][:2], "seat %d's client and the host's arena of that seat part at tick %d" % (ind, t)
+        assert theirs[n - 1][0] == mine[ind][n - 1][0]  # both copies end (or are cut off) in the same state

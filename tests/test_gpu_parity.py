@@ -431,9 +431,11 @@ def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):
 
 
 def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
-    """SURVEY 8f rank 3 (started): a match hosted with the reference server's wire protocol
-    (strikeforce_b200.match_server) whose authoritative arena lives on the GPU; two scripted socket
-    clients and one host-played seat, the arena compared with the oracle fed the relayed commands."""
+    """SURVEY 8f rank 3: a match hosted with the reference server's wire protocol
+    (strikeforce_b200.match_server) whose arenas live on the GPU -- one per SEAT (sf_config.royale_ind):
+    the copy of the match each seat's own client holds, kill credits and corpses included; two scripted
+    socket clients and one host-played seat, every seat's arena compared with the oracle of that seat fed
+    the relayed commands."""
     import socket
     import threading
     import test_match_server as tms
@@ -458,17 +460,24 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
         tms.wait_for_seat(host, seat)
     lobby.join(20)
     host.handshake()
-    sim = BatchedArena(1, mode="Royale", teams=teams, auto_reset=False)
-    cfg = sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False)
-    o = sfo.Arena(cfg)
-    o.reset(1, tb, serial)
+    sims = [BatchedArena(1, mode="Royale", teams=teams, auto_reset=False, ind=s) for s in range(3)]
+    sim = sims[0]
+    oracles = []
+    for s in range(3):
+        oa = sfo.Arena(sfcfg.make_config(arena_data, mode=sfcfg.MODE_ROYALE, teams=teams, auto_reset=False, ind=s))
+        oa.reset(1, tb, serial)
+        oracles.append(oa)
+    o = oracles[0]
     try:
-        sim.reset([0], [tb], [serial])
+        for sm in sims:
+            sm.reset([0], [tb], [serial])
         tick = [0]
 
         def step(row):
-            sim.step(torch.tensor(list(row), dtype=torch.uint8, device=sim.device).view(1, 3))
-            o.step(row)
+            for sm, oa in zip(sims, oracles):
+                sm.step(torch.tensor(list(row), dtype=torch.uint8, device=sm.device).view(1, 3))
+                oa.step(row)
+                assert np.uint64(sm.state_hash().cpu().numpy().view(np.uint64)[0]) == np.uint64(oa.state_hash())
 
         def policy(seat):
             tick[0] += 1
@@ -481,4 +490,6 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
             c.join(10)
             assert c.error is None and len(c.received) == T
     finally:
-        sim.close(), host.close(), listener.close()
+        for sm in sims:
+            sm.close()
+        host.close(), listener.close()

@@ -1,14 +1,14 @@
-"""Match-server bridge -- started; the wire protocol is pinned against the
-reference's own client code, the rules that depend on whose copy a match is are not yet.
+"""Match-server bridge: the reference's match server with arenas attached.
 
 The reference's match server (StrikeForce-server/server.cpp) only relays: it accepts ``n`` players,
 tells everyone the seeds and the roster, and then, tick by tick, collects one command byte from every
 live player and sends each player the bytes of the others; every client steps its own copy of the
 match, which stays identical because the tick is deterministic (client side: gameplay.hpp:66-193).
 ``MatchHost`` speaks that protocol and can additionally fill seats itself (``local_seats``: players
-whose commands come from the host, e.g. device-side agents) and hand every tick's command row to an
-arena of its own (``BatchedArena`` in Battle Royale mode) -- a GPU-hosted match that stock clients
-can join, because the device tick is bit-exact.
+whose commands come from the host, e.g. device-side agents) and hand every tick's command row to
+arenas of its own (``BatchedArena`` in Battle Royale mode, one per seat with ``ind`` = that seat: the
+copy of the match that seat's client holds) -- a GPU-hosted match that stock clients can join, because
+the device tick is bit-exact.
 
 Wire format, all messages NUL-terminated (server.cpp):
   :199-213  client -> password; server -> "A" or "R"
@@ -19,16 +19,18 @@ Wire format, all messages NUL-terminated (server.cpp):
             server -> to every live client the bytes of all other live players, in index order
             (plus, once, the '_' of a player that just quit)
   :108-132  the match ends when the live players' teams no longer change along the index order
+  :265-279  every match socket has a 500 ms receive time-out; a socket that fails plays '_'
 
 Pinning (tests/test_match_server.py): processes running the UNMODIFIED reference client (its
 network code through oracle/ref_harness: client.start / give_info / get_info / send_it / recieve)
-join a hosted match and every tick their copy of the match equals the host's arena, up to the header
-field that says which player the copy belongs to (400 ticks of commands that never attack).  With
-the whole alphabet (1,500 ticks) the client in seat 0 -- the seat whose copy the host's arena is --
-still matches completely, the other one in everything but the header counters and the cells: the few
-rules that depend on `ind` (kill and loot credits, the own corpse keeping its cell, gameplay.hpp
-:591-592, 629-630, 642-645) differ between the copies by design.  Scripted socket clients check the
-bytes of quits, eliminations and the winner.
+join a hosted match; the host keeps one arena per seat, and every tick the copy of the match each
+client computes equals the host's arena of that client's seat COMPLETELY -- 400 ticks of commands
+that never attack, and 1,500 ticks of the whole alphabet, where the rules that depend on whose copy
+it is come into play (kill and loot credits, the own corpse keeping its cell, gameplay.hpp:591-592,
+629-630, 642-645).  Scripted socket clients check the bytes of quits, eliminations and the winner,
+and that a client which goes silent is dropped after the time-out instead of freezing the match.
+Still open: matches that are played to their natural end against live clients (the scripted ones end;
+the live ones are cut off at a tick limit unless a copy ends by the death of its player).
 """
 from __future__ import annotations
 

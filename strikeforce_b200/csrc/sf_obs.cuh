@@ -96,7 +96,10 @@ SF_FN void sf_describe_cell(const SfDev &d, const SfConst &k, int env, const SfE
         f[15] = 1000;
     if (s0) {
         int dmg, eff;
-        f[20 + (int)(SF_AT(d.h_pw, occ) >> POS_HI_SHIFT)] = 1000;
+        {   /* static subscripts only: f[] stays in registers */
+            const int wy = (int)(SF_AT(d.h_pw, occ) >> POS_HI_SHIFT);
+            f[20] = wy == 0 ? 1000 : 0, f[21] = wy == 1 ? 1000 : 0, f[22] = wy == 2 ? 1000 : 0, f[23] = wy == 3 ? 1000 : 0;
+        }
         sf_damage_effect(d, k, env, e, occ, &dmg, &eff);
         f[24] = dmg, f[25] = -eff, f[26] = SF_AT(d.h_stam, occ);
     } else if (s1) {
@@ -107,7 +110,8 @@ SF_FN void sf_describe_cell(const SfDev &d, const SfConst &k, int env, const SfE
         {
             uint32_t meta = SF_AT(d.b_meta, bidx);
             int range = (int)(meta & 0xFFu), trav = (int)((meta >> 8) & 0xFFu);
-            f[20 + (int)(SF_AT(d.b_pw, bidx) >> POS_HI_SHIFT)] = 10 * (range - trav); /* (range - dist) / 100.0 */
+            const int wy = (int)(SF_AT(d.b_pw, bidx) >> POS_HI_SHIFT), left = 10 * (range - trav); /* (range - dist) / 100.0 */
+            f[20] = wy == 0 ? left : 0, f[21] = wy == 1 ? left : 0, f[22] = wy == 2 ? left : 0, f[23] = wy == 3 ? left : 0;
             f[24] = SF_AT(d.b_dmg, bidx), f[25] = -SF_AT(d.b_eff, bidx);
         }
     } else if (s7) {

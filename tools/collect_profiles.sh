@@ -33,11 +33,8 @@ ncu -i gpurun_out/${TAG}_obs.ncu-rep --page raw --csv 2>/dev/null > profiles/${T
 python tools/ncu_mem_lines.py /tmp/${TAG}_src_step.csv > profiles/${TAG}_step_kernel_mem_lines.txt 2>/dev/null || true
 # SASS evidence: instruction mix per kernel of the shipped library (no tensor-core ops: there is no contraction on this path)
 {
-  echo "# cuobjdump -sass strikeforce_b200/libstrikeforce_b200.so: instructions per kernel and the mnemonics that matter"
-  cuobjdump -sass strikeforce_b200/libstrikeforce_b200.so | awk '
-    /Function : /{name=$3}
-    /^ +\/\*[0-9a-f]+\*\/ /{n[name]++; m=$2; if (m ~ /^@/) m=$3; sub(/\..*/,"",m); c[name" "m]++}
-    END{for(k in n) print n[k], k; for(k in c) print "  ", c[k], k}' | sort -k2,2 -k1,1nr | awk '$1=="" || $2 ~ /^(LDS|STS|LDG|STG|LDL|STL|BAR|REDUX|ATOMS|ATOMG|RED|SHFL|VOTE|HMMA|IMMA|UTCMMA|UBLKCP|UTMA|BSSY|CALL|IMAD|LOP3|ISETP)$/ || NF==2'
+  echo "# tools/sass_summary.py strikeforce_b200/libstrikeforce_b200.so (cuobjdump -sass): instructions per kernel and what they are made of"
+  python tools/sass_summary.py strikeforce_b200/libstrikeforce_b200.so
 } > profiles/${TAG}_sass_summary.txt
 python - <<PY
 import csv, json

@@ -28,9 +28,9 @@ client computes equals the host's arena of that client's seat COMPLETELY -- 400 
 that never attack, and 1,500 ticks of the whole alphabet, where the rules that depend on whose copy
 it is come into play (kill and loot credits, the own corpse keeping its cell, gameplay.hpp:591-592,
 629-630, 642-645).  Scripted socket clients check the bytes of quits, eliminations and the winner,
-and that a client which goes silent is dropped after the time-out instead of freezing the match.
-Still open: matches that are played to their natural end against live clients (the scripted ones end;
-the live ones are cut off at a tick limit unless a copy ends by the death of its player).
+that a client which goes silent is dropped after the time-out instead of freezing the match, and a
+match between two live reference clients is left alone until it is over (a player falls, its client
+reports '~', result() names the winner) with every copy equal to the host's arena of its seat to the end.
 """
 from __future__ import annotations
 

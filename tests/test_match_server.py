@@ -135,6 +135,7 @@ def test_protocol_roster_relay_quit_and_winner(arena_data):
 CLIENT_SCRIPT = """
 import os, sys, zlib
 root, port, ticks, table = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4].encode()
+sys.stdout = open(sys.argv[5], "w")  # a file, not a pipe: nobody reads while the match runs, and a full pipe would stall this client into the server's time-out
 for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
     sys.path.insert(0, p)
 import common, sfref
@@ -169,8 +170,11 @@ def _hosted_match_with_reference_clients(arena_data, table, T):
     host = ms.MatchHost(teams, "pw", tb, serial)
     lobby = threading.Thread(target=host.accept, args=(listener,), daemon=True)
     lobby.start()
-    procs = [subprocess.Popen([sys.executable, "-c", CLIENT_SCRIPT, root, str(port), str(T), table.decode()],
-                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in teams]
+    import tempfile
+    outdir = tempfile.mkdtemp()
+    outs = [os.path.join(outdir, "client%d.txt" % i) for i in range(len(teams))]
+    procs = [subprocess.Popen([sys.executable, "-c", CLIENT_SCRIPT, root, str(port), str(T), table.decode(), outs[i]],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for i in range(len(teams))]
     try:
         lobby.join(120)
         assert sorted(host.socks) == [0, 1]
@@ -194,8 +198,9 @@ def _hosted_match_with_reference_clients(arena_data, table, T):
 
         winner, ticks = ms.host_match(host, step, max_ticks=T)
         results = {}
-        for p in procs:
-            out, err = p.communicate(timeout=120)
+        for p, path in zip(procs, outs):
+            _, err = p.communicate(timeout=120)
+            out = open(path).read()
             ind = int([l for l in out.splitlines() if l.startswith("IND")][0].split()[1])
             lines = [l.split() for l in out.splitlines() if l.startswith("H ")]
             assert lines, out[-500:] + err[-2000:]
@@ -288,3 +293,23 @@ def test_reference_clients_fight_in_a_hosted_match(arena_data):
         for t in range(n):
             assert theirs[t][:2] == mine[ind][t][:2], "seat %d's client and the host's arena of that seat part at tick %d" % (ind, t)
         assert theirs[n - 1][0] == mine[ind][n - 1][0]  # both copies end (or are cut off) in the same state
+
+
+def test_reference_clients_play_a_hosted_match_to_its_end(arena_data):
+    """The same match left alone until it is over: with random commands the zombies and NPC humans of the
+    arena sooner or later kill a player, its client's check_end() reports '~' (gameplay.hpp:1131-1136) and
+    leaves, and the server's result() (server.cpp:108-132) names the team of the player that is left.  Every
+    client's copy equals the host's arena of its seat up to the tick its copy ends, with the same final status."""
+    T = 12000
+    mine, results, winner, ticks = _hosted_match_with_reference_clients(arena_data, sfcfg.ACTIONS28, T)
+    assert ticks < T and winner in (1, 2), "the match did not end by itself (winner %d after %d ticks)" % (winner, ticks)
+    ended = 0
+    for ind, theirs in results.items():
+        n = min(len(mine[ind]), len(theirs))
+        assert n >= 200
+        for t in range(n):
+            assert theirs[t][:2] == mine[ind][t][:2], "seat %d at tick %d" % (ind, t)
+        ended += theirs[-1][0] != 0
+        if theirs[-1][0] != 0:  # that copy ended: DEAD for the player that fell, the host's arena of the seat agrees
+            assert len(theirs) <= len(mine[ind]) and mine[ind][len(theirs) - 1][0] == theirs[-1][0]
+    assert ended >= 1

@@ -302,7 +302,23 @@ def run_ours(args):
         barrier()
         ms_obs_only = eo[0].elapsed_time(eo[1])
         ms_both = eo[1].elapsed_time(eo[2])
-        obs_row = (KO, ms_obs_only, ms_both)
+        # the same observations with the channel innermost (SF_OBS_NHWC: what the policy's convolutions read
+        # without a transpose; the reference's own layout is the one above)
+        ec = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        sim.observe(1, out=obs_buf, channels_last=True)
+        barrier()
+        torch.cuda.nvtx.range_push("sf_timed_observe_nhwc")
+        ec[0].record()
+        for i in range(KO):
+            sim.observe(1, out=obs_buf, channels_last=True)
+        ec[1].record()
+        torch.cuda.nvtx.range_pop()
+        for i in range(KO):
+            sim.observe(1, out=obs_buf, channels_last=True)
+            sim.step(acts_o[i])
+        ec[2].record()
+        barrier()
+        obs_row = (KO, ms_obs_only, ms_both, ec[0].elapsed_time(ec[1]), ec[1].elapsed_time(ec[2]))
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
@@ -346,7 +362,7 @@ def run_ours(args):
             "rng_draws_per_env_step": d_dev["rng_draws"] / max(1, steps_done),
         }
         if obs_row is not None:
-            KO, ms_obs_only, ms_both = obs_row
+            KO, ms_obs_only, ms_both, ms_cl_only, ms_cl_both = obs_row
             obs_bytes = E * sfcfg.OBS_LEN * 4
             line["with_observation"] = {
                 "note": "rank 0; one fp32 [32,31,31] observation of the player per arena per step, written to HBM",
@@ -355,7 +371,14 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "kernel": "sf_observe_kernel", "achieved": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": obs_bytes / (ms_obs_only / KO / 1e3) / 1e9 / peak,
                              "traffic": load_traffic("sf_observe_kernel", E),
-                             "algo_bytes_per_observation": sfcfg.OBS_LEN * 4}}
+                             "algo_bytes_per_observation": sfcfg.OBS_LEN * 4},
+                "channels_last": {
+                    "note": "the same values written [31][31][32] per observation (SF_OBS_NHWC, sf_observe_kernel<true>)",
+                    "value_step_plus_obs": KO * E / (ms_cl_both / 1e3), "ms_per_step": ms_cl_both / KO,
+                    "observe_kernel_ms": ms_cl_only / KO,
+                    "roofline": {"bound": "hbm", "kernel": "sf_observe_kernel<NHWC>", "achieved": obs_bytes / (ms_cl_only / KO / 1e3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": obs_bytes / (ms_cl_only / KO / 1e3) / 1e9 / peak,
+                                 "traffic": load_traffic("sf_observe_kernel_nhwc", E)}}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(args.cpu_steps, overhead=True)
         print(json.dumps(line))
@@ -434,19 +457,24 @@ def run_royale(args):
             for i in range(8)]
     it = iter(range(10 ** 9))
     ms_step = timed(lambda: sim.step(acts[next(it) % len(acts)]), 4 * K, W)
-    obs = torch.empty((E, P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32, device=sim.device)
+    # the observations are written channel-innermost (SF_OBS_NHWC: same values, [31][31][32] per observation) so
+    # that the first convolution reads them as they are; --nchw keeps the reference's [32][31][31]
+    cl = not args.nchw
+    obs = torch.empty((E, P, sfcfg.OBS_WIN, sfcfg.OBS_WIN, sfcfg.OBS_CH) if cl else
+                      (E, P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32, device=sim.device)
     mask = (1 << P) - 1
-    ms_observe = timed(lambda: sim.observe(mask, out=obs), 2 * K, W)
+    ms_observe = timed(lambda: sim.observe(mask, out=obs, channels_last=cl), 2 * K, W)
     model = policy.AgentModel().to(sim.device)
-    agent = policy.PolicyAgent(model, E * P, device=sim.device, seed=1 + rank, chunk=args.policy_chunk, t_initial=0)
-    custom = bots.Custom(agent).prepare(sim)
+    agent = policy.PolicyAgent(model, E * P, device=sim.device, seed=1 + rank, chunk=args.policy_chunk, t_initial=0,
+                               channels_last=cl)
+    custom = bots.Custom(agent, channels_last=cl).prepare(sim)
     actions = torch.empty((E, P), dtype=torch.uint8, device=sim.device)
     l0 = sim.launches
 
     def tick():
-        sim.observe(mask, out=obs)
+        o = sim.observe(mask, out=obs, channels_last=cl)
         with torch.no_grad():
-            idx = agent.predict(obs.view(E * P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN))
+            idx = agent.predict(o.flatten(0, 1))
         actions.copy_(custom._table[idx].view(E, P))
         sim.step(actions)
         custom.new_games(sim, sim.step_out()[:, 0] != sfcfg.RUNNING)
@@ -468,7 +496,7 @@ def run_royale(args):
             "metric": METRIC, "value": world * E / (ms_tick / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_tick, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (tick), fp32 policy" + ("" if args.strict_fp32 else " with TF32 convolutions (cuDNN default)"),
             "data": "synthetic (seeded matches, random-init policy weights)",
-            "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P),
+            "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P, observation_layout="nhwc" if cl else "nchw"),
             "setup": {"prewarm_steps": min(args.prewarm, 512),
                       "mean_population": dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"], [round(x, 2) for x in pop]))},
             "e2e": {"value": world * E / (ms_play / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 128 // max(1, K),
@@ -536,6 +564,8 @@ def main():
                          "their observations and one batched policy forward every tick (use --steps 3)")
     ap.add_argument("--policy-chunk", type=int, default=32768, help="royale16: observations per forward call")
     ap.add_argument("--strict-fp32", action="store_true", help="royale16: convolutions without TF32 (8x slower)")
+    ap.add_argument("--nchw", action="store_true", help="royale16: observations in the reference's [32][31][31] layout "
+                                                        "(default: channel innermost, SF_OBS_NHWC)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

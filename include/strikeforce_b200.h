@@ -137,7 +137,12 @@ enum {
 
 /* observation points */
 enum { SF_OBS_P1 = 1 /* loop top, get_my_action gameplay.hpp:956 */,
-       SF_OBS_P2 = 2 /* inside human_action, get_command gameplay.hpp:933 */ };
+       SF_OBS_P2 = 2 /* inside human_action, get_command gameplay.hpp:933 */,
+       /* OR-ed into the phase: the same values with the channel innermost, [n_envs][n_obs_agents][31][31][32]
+          (what a convolution library calls NHWC / channels-last; the reference's tensor, Custom.hpp:139, is
+          [32][31][31]).  The policy's first convolution then reads the buffer as it is instead of
+          transposing 123,008 bytes per observation first. */
+       SF_OBS_NHWC = 0x100 };
 
 /* Replaces: the process-wide `gameplay g` and its globals (gameplay.hpp:47-55, 1739). */
 int sf_create(const sf_config *cfg, sf_handle **out);
@@ -178,7 +183,8 @@ int sf_synth_actions(sf_handle *h, uint8_t *actions, uint64_t t, const char *tab
 
 /* Replaces gameplay::bot() up to the Agent::predict call (bots/bot-0.5/Custom.hpp:137-158):
    writes the fp32 [n_envs][n_obs_agents][32][31][31] observation of the driven humans into the
-   DEVICE buffer obs.  agent_mask bit a selects human slot a (bit 0 = the player).  phase names the
+   DEVICE buffer obs ([..][31][31][32] with phase | SF_OBS_NHWC).  agent_mask bit a selects human slot a
+   (bit 0 = the player).  phase names the
    observation point the caller is at and must match the handle: SF_OBS_P2 between sf_step_a and
    sf_step_b, SF_OBS_P1 otherwise (SF_ERR_ARG if it does not). */
 int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, void *stream);

@@ -65,8 +65,9 @@ class Custom:
 
     action = sfcfg.ACTIONS9  # gameplay::action = "+xzqeawsd", Custom.hpp:162
 
-    def __init__(self, agent: Agent | None = None):
+    def __init__(self, agent: Agent | None = None, channels_last=False):
         self.agent = agent
+        self.channels_last = channels_last  # the layout sf_observe writes (SF_OBS_NHWC); shape and values are the same
         self._table = None
 
     def prepare(self, sim):
@@ -77,9 +78,9 @@ class Custom:
 
     def bot(self, sim, agent_mask=1, phase=sfcfg.OBS_P1):
         """uint8 device tensor [n_envs, n_selected] of command symbols for the selected humans."""
-        obs = sim.observe(agent_mask, phase)
+        obs = sim.observe(agent_mask, phase, channels_last=self.channels_last)
         n_envs, nsel = obs.shape[0], obs.shape[1]
-        idx = self.agent.predict(obs.view(n_envs * nsel, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN))
+        idx = self.agent.predict(obs.flatten(0, 1))
         self.agent.update(idx, False)
         return self._table[idx].view(n_envs, nsel)
 

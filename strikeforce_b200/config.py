@@ -29,6 +29,7 @@ RUNNING, WIN, DEAD, TIMEOUT, TRUNCATED, OVERFLOW, UB_GUARD = range(7)
 STATUS_NAMES = ["running", "win", "dead", "timeout", "truncated", "overflow", "ub_guard"]
 
 OBS_P1, OBS_P2 = 1, 2
+OBS_NHWC = 0x100  # OR-ed into the phase: channel innermost
 
 FIELD_STEP_OUT, FIELD_STATE_HASH, FIELD_COUNTERS, FIELD_POPULATION, FIELD_STATS = 1, 2, 3, 4, 5
 STAT_NAMES = ["steps", "episodes", "wins", "deaths", "timeouts", "truncated", "overflows", "ub_guards",

@@ -249,9 +249,10 @@ __device__ __forceinline__ void sf_obs_item(int item, int nsel, uint32_t agent_m
     *env = item / nsel, *slot = __ffs(m) - 1;
 }
 
+template <bool NHWC> /* NHWC: the same values with the channel innermost, SF_OBS_NHWC of the header */
 __global__ void __launch_bounds__(SF_OBS_CTA, SF_OBS_CTAS_PER_SM)
 sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
-                  int nsel, int n_items)
+                  int nsel, int n_items, int rows)
 {
     float *feat = reinterpret_cast<float *>(sf_smem);                         /* [row][SF_OBS_PITCH] */
     uint16_t *code = reinterpret_cast<uint16_t *>(feat + SF_OBS_ROWS * SF_OBS_PITCH); /* per window cell */
@@ -334,15 +335,15 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                 uint32_t cd = (cv[q] >> 16) & 0xFu; /* M_WALL | M_UP | M_DOWN | M_EXIT: rows 1..15 of the table */
                 if (dyn) {
                     const int i = base + __popc(md & ((1u << lane) - 1u));
-                    cd = i < SF_OBS_CACHE ? 16u + (uint32_t)i : SF_OBS_BEYOND;
-                    if (i < SF_OBS_CACHE) dlist[i] = (uint16_t)w;
+                    cd = i < rows ? 16u + (uint32_t)i : SF_OBS_BEYOND;
+                    if (i < rows) dlist[i] = (uint16_t)w;
                 }
                 code[w] = (uint16_t)cd;
             }
         }
         __syncthreads();
         /* describe() once per dynamic cell; its 32 transformed features become a table row */
-        const int n_dyn = *count < SF_OBS_CACHE ? *count : SF_OBS_CACHE;
+        const int n_dyn = *count < rows ? *count : rows;
         for (int i = threadIdx.x; i < n_dyn; i += SF_OBS_CTA) {
             const int w = dlist[i], cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
             int32_t f[32];
@@ -356,6 +357,31 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
            chunks first and the others in a second pass, lane-dense (41% slower: partial-warp stores); a
            warp vote that sends 128 empty cells in a row down a store-only path (7% slower) */
         float4 *dst = reinterpret_cast<float4 *>(out);
+        if constexpr (NHWC) {
+            /* channel-innermost: the 32 features of a cell are one table row = eight chunks; chunk idx
+               covers features 4p..4p+3 of window cell idx / 8 */
+#pragma unroll 4
+            for (int idx = threadIdx.x; idx < SF_OBS_CELLS * (SF_OBS_CH / 4); idx += SF_OBS_CTA) {
+                const int w = idx / (SF_OBS_CH / 4), p = idx % (SF_OBS_CH / 4);
+                const uint32_t cd = code[w];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cd == SF_OBS_BEYOND) { /* more dynamic cells than table rows (rare) */
+                    const int cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
+                    int32_t f[32];
+                    sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
+                    int32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+#pragma unroll
+                    for (int c = 0; c < SF_OBS_CH / 4; ++c)
+                        if (c == p) g0 = f[4 * c], g1 = f[4 * c + 1], g2 = f[4 * c + 2], g3 = f[4 * c + 3];
+                    v.x = g0 ? sf_obs_transform(d, g0, &fb) : 0.f, v.y = g1 ? sf_obs_transform(d, g1, &fb) : 0.f;
+                    v.z = g2 ? sf_obs_transform(d, g2, &fb) : 0.f, v.w = g3 ? sf_obs_transform(d, g3, &fb) : 0.f;
+                } else if (cd) {
+                    const float *r = feat + cd * SF_OBS_PITCH + 4 * p;
+                    v = make_float4(r[0], r[1], r[2], r[3]);
+                }
+                __stcs(dst + idx, v);
+            }
+        } else
         for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
             int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
             int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
@@ -400,200 +426,10 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
     if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
 }
 
-/* ---- the same kernel, warp-specialised (-DSF_OBS_WS) --------------------------------------
- * The single-role kernel above alternates between describing a window (dependent loads, barriers)
- * and streaming it out (stores): while a CTA does one it does not do the other.  Here a CTA of 256
- * threads is split into four PRODUCER warps that describe window i+1 into one of two description
- * buffers (codes + feature table) and four CONSUMER warps that stream window i out of the other;
- * the hand-off is a pair of named barriers per buffer (full / empty), bar.arrive on the side that
- * does not wait. */
-#define SF_OBSW_CTA 256
-#ifndef SF_OBSW_CTAS_PER_SM
-#define SF_OBSW_CTAS_PER_SM 4
-#endif
-#define SF_OBSW_HALF 128
-struct SfObsHeader { /* what the consumers need of a window besides codes and table (only for cells beyond the table) */
-    int env, vcell, level, hw_h;
-    uint32_t team, ntemp;
-    uint64_t mb0, mb1;
-};
-#define SF_OBSW_BUF (SF_OBS_ROWS * SF_OBS_PITCH * 4 + 3 * SF_OBS_LIST * 2 + 64) /* table | code | bmap | tmap | header */
-#define SF_OBSW_SMEM (2 * SF_OBSW_BUF + SF_OBS_LIST * 2 + 16)
-static_assert(SF_OBSW_BUF % 16 == 0 && sizeof(SfObsHeader) <= 64, "buffers stay 16-byte aligned");
-
-__device__ __forceinline__ void sf_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void sf_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-enum { SF_BAR_FULL = 1, SF_BAR_EMPTY = 3, SF_BAR_PRODUCERS = 5 };
-
-__global__ void __launch_bounds__(SF_OBSW_CTA, SF_OBSW_CTAS_PER_SM)
-sf_observe_ws_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
-                     int nsel, int n_items)
-{
-    uint16_t *dlist = reinterpret_cast<uint16_t *>(sf_smem + 2 * SF_OBSW_BUF);
-    int *count = reinterpret_cast<int *>(dlist + SF_OBS_LIST);
-    SfTabs t;
-    sf_global_tabs(d, t);
-    uint32_t fb = 0;
-    const bool producer = threadIdx.x < SF_OBSW_HALF;
-    const int tid = threadIdx.x & (SF_OBSW_HALF - 1);
-    if (threadIdx.x < 32) { /* rows 1..15 of both tables: describe() of a cell with nothing on it */
-        const int st = threadIdx.x & 15, b = threadIdx.x >> 4;
-        float *feat = reinterpret_cast<float *>(sf_smem + b * SF_OBSW_BUF);
-        SfEnv e0;
-        e0.mb[0] = e0.mb[1] = 0, e0.ntemp = 0, e0.level = 1, e0.hw_h = 0, e0.env = 0;
-        int32_t f[32];
-        sf_describe_cell(d, k, 0, e0, 0, st, 0u, 0u, -1, -1, f);
-#pragma unroll
-        for (int c = 0; c < SF_OBS_CH; ++c) feat[st * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
-    }
-    __syncthreads();
-    if (!producer) { /* both buffers start empty */
-        sf_bar_arrive(SF_BAR_EMPTY + 0, SF_OBSW_CTA);
-        sf_bar_arrive(SF_BAR_EMPTY + 1, SF_OBSW_CTA);
-    }
-    constexpr int PER = (SF_OBS_CELLS + SF_OBSW_HALF - 1) / SF_OBSW_HALF;
-    int round = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++round) {
-        const int b = round & 1;
-        float *feat = reinterpret_cast<float *>(sf_smem + b * SF_OBSW_BUF);
-        uint16_t *code = reinterpret_cast<uint16_t *>(feat + SF_OBS_ROWS * SF_OBS_PITCH);
-        int16_t *bmap = reinterpret_cast<int16_t *>(code + SF_OBS_LIST);
-        int16_t *tmap = bmap + SF_OBS_LIST;
-        SfObsHeader *hdr = reinterpret_cast<SfObsHeader *>(tmap + SF_OBS_LIST);
-        if (producer) {
-            int env, slot;
-            sf_obs_item(item, nsel, agent_mask, &env, &slot);
-            SfEnv e;
-            const uint32_t misc = d.misc[env];
-            e.level = (int)(misc & 0xFFu), e.hw_h = (int)((misc >> 16) & 0xFFu);
-            e.mb[0] = SF_AT(d.mb, 0), e.mb[1] = SF_AT(d.mb, 1);
-            e.ntemp = d.ntemp[env];
-            e.env = env;
-            const bool observer = slot < e.hw_h;
-            const int vcell = observer ? (int)(SF_AT(d.h_pw, slot) & POS_CELL) : 0;
-            const uint32_t team = observer ? (SF_AT(d.h_sel, slot) & HS_TEAM) : 0u;
-            int vf, vr, vc;
-            sf_tcell_decode(vcell, &vf, &vr, &vc);
-            const int r0 = vr - SF_OBS_R, c0 = vc - SF_OBS_R;
-            uint32_t cv[PER];
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int w = tid + q * SF_OBSW_HALF;
-                const int cell = (observer && w < SF_OBS_CELLS) ? sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN) : -1;
-                cv[q] = cell >= 0 ? ((uint32_t)SF_G(cell) | ((uint32_t)t.smap[cell] << 16)) : 0u;
-            }
-            sf_bar_sync(SF_BAR_EMPTY + b, SF_OBSW_CTA); /* the consumers are done with this buffer */
-            for (int i = tid; i < SF_OBS_CELLS; i += SF_OBSW_HALF) bmap[i] = -1, tmap[i] = -1;
-            if (tid == 0) {
-                *count = 0;
-                hdr->env = env, hdr->vcell = vcell, hdr->level = e.level, hdr->hw_h = e.hw_h, hdr->team = team, hdr->ntemp = e.ntemp;
-                hdr->mb0 = e.mb[0], hdr->mb1 = e.mb[1];
-            }
-            sf_bar_sync(SF_BAR_PRODUCERS, SF_OBSW_HALF);
-            if (observer) {
-                for (int bl = tid; bl < SF_LIM_BULLETS; bl += SF_OBSW_HALF)
-                    if (m2_test(e.mb, bl) && (SF_AT(d.b_meta, bl) & BF_OWNS)) {
-                        int bf, br, bc;
-                        sf_tcell_decode((int)(SF_AT(d.b_pw, bl) & POS_CELL), &bf, &br, &bc);
-                        int wi = br - r0, wj = bc - c0;
-                        if (bf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
-                            bmap[wi * SF_OBS_WIN + wj] = (int16_t)bl;
-                    }
-                for (int q = tid; q < (int)e.ntemp; q += SF_OBSW_HALF) {
-                    int tf, tr, tc;
-                    sf_tcell_decode((int)SF_T(d.t_cell, q), &tf, &tr, &tc);
-                    int wi = tr - r0, wj = tc - c0;
-                    if (tf == vf && wi >= 0 && wi < SF_OBS_WIN && wj >= 0 && wj < SF_OBS_WIN)
-                        tmap[wi * SF_OBS_WIN + wj] = (int16_t)q;
-                }
-            }
-            sf_bar_sync(SF_BAR_PRODUCERS, SF_OBSW_HALF);
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int w = tid + q * SF_OBSW_HALF;
-                const bool dyn = w < SF_OBS_CELLS && ((cv[q] & 0xFFFFu) || bmap[w] >= 0);
-                const unsigned md = __ballot_sync(0xffffffffu, dyn);
-                const unsigned lane = threadIdx.x & 31u;
-                int base = 0;
-                if (lane == 0 && md) base = atomicAdd(count, __popc(md));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (w < SF_OBS_CELLS) {
-                    uint32_t cd = (cv[q] >> 16) & 0xFu;
-                    if (dyn) {
-                        const int i = base + __popc(md & ((1u << lane) - 1u));
-                        cd = i < SF_OBS_CACHE ? 16u + (uint32_t)i : SF_OBS_BEYOND;
-                        if (i < SF_OBS_CACHE) dlist[i] = (uint16_t)w;
-                    }
-                    code[w] = (uint16_t)cd;
-                }
-            }
-            sf_bar_sync(SF_BAR_PRODUCERS, SF_OBSW_HALF);
-            const int n_dyn = *count < SF_OBS_CACHE ? *count : SF_OBS_CACHE;
-            for (int i = tid; i < n_dyn; i += SF_OBSW_HALF) {
-                const int w = dlist[i], cell = sf_obs_cell(vcell, w / SF_OBS_WIN, w % SF_OBS_WIN);
-                int32_t f[32];
-                sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[w], tmap[w], f);
-#pragma unroll
-                for (int c = 0; c < SF_OBS_CH; ++c) feat[(16 + i) * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
-            }
-            sf_bar_sync(SF_BAR_PRODUCERS, SF_OBSW_HALF); /* dlist and count are reused by the next window */
-            __threadfence_block();
-            sf_bar_arrive(SF_BAR_FULL + b, SF_OBSW_CTA);
-        } else {
-            sf_bar_sync(SF_BAR_FULL + b, SF_OBSW_CTA);
-            float4 *dst = reinterpret_cast<float4 *>(obs + (size_t)item * SF_OBS_LEN);
-            for (int q = tid; q < SF_OBS_GROUP; q += SF_OBSW_HALF) {
-                int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS;
-                int row[4];
-                bool beyond = false;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t cd = code[w];
-                    row[j] = cd ? (int)cd * SF_OBS_PITCH + cc : -1;
-                    if (cd == SF_OBS_BEYOND) beyond = true, row[j] = -2 - w;
-                    if (++w == SF_OBS_CELLS) w = 0, ++cc;
-                }
-                if (!beyond) {
-#pragma unroll
-                    for (int g = 0; g < SF_OBS_CH / 4; ++g) {
-                        float4 v;
-                        v.x = row[0] >= 0 ? feat[row[0] + 4 * g] : 0.f;
-                        v.y = row[1] >= 0 ? feat[row[1] + 4 * g] : 0.f;
-                        v.z = row[2] >= 0 ? feat[row[2] + 4 * g] : 0.f;
-                        v.w = row[3] >= 0 ? feat[row[3] + 4 * g] : 0.f;
-                        __stcs(dst + g * SF_OBS_GROUP + q, v);
-                    }
-                } else { /* more dynamic cells than table rows (rare): described here from the window's header */
-                    SfEnv e;
-                    e.level = hdr->level, e.hw_h = hdr->hw_h, e.mb[0] = hdr->mb0, e.mb[1] = hdr->mb1, e.ntemp = hdr->ntemp, e.env = hdr->env;
-                    const int env = hdr->env;
-                    float val[4][SF_OBS_CH / 4];
-                    int cj = (4 * q) / SF_OBS_CELLS, wj = 4 * q - cj * SF_OBS_CELLS;
-#pragma unroll 1
-                    for (int j = 0; j < 4; ++j) {
-                        if (row[j] <= -2) {
-                            const int cell = sf_obs_cell(hdr->vcell, wj / SF_OBS_WIN, wj % SF_OBS_WIN);
-                            int32_t f[32];
-                            sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), hdr->team, bmap[wj], tmap[wj], f);
-                            for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = f[4 * g + cj] ? sf_obs_transform(d, f[4 * g + cj], &fb) : 0.f;
-                        } else {
-                            for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = row[j] >= 0 ? feat[row[j] + 4 * g] : 0.f;
-                        }
-                        if (++wj == SF_OBS_CELLS) wj = 0, ++cj;
-                    }
-                    for (int g = 0; g < SF_OBS_CH / 4; ++g)
-                        __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
-                }
-            }
-            sf_bar_arrive(SF_BAR_EMPTY + b, SF_OBSW_CTA);
-        }
-    }
-    if (producer) { /* consume the last "empty" arrivals so that no barrier is left half-filled at exit */
-        sf_bar_sync(SF_BAR_EMPTY + (round & 1), SF_OBSW_CTA);
-        sf_bar_sync(SF_BAR_EMPTY + ((round + 1) & 1), SF_OBSW_CTA);
-    }
-    if (fb) atomicAdd(&d.stats[SF_STAT_RESERVED0], (unsigned long long)fb);
-}
+/* Measured and rejected (profiles/r02_variants.txt; the code is in the history of this file): a
+   warp-specialised version of this kernel -- four producer warps describing window i+1 into one of two
+   description buffers while four consumer warps stream window i out of the other, named barriers in
+   between -- 4.80 ms against 3.71 ms: half the CTA's threads issue no stores. */
 
 /* Random::_srand + n _rand() draws for a batch of independent streams (random.hpp:54-76) */
 __global__ void __launch_bounds__(SF_CTA, 1)
@@ -636,6 +472,7 @@ struct sf_handle {
     int device = 0, n_sm = 0;
     bool between_halves = false; /* sf_step_a has run, sf_step_b has not: the P2 observation point */
     int lanes_per_warp = 0;      /* 0 = chosen from the batch size; SF_LANES_PER_WARP overrides (measurements) */
+    int obs_rows = SF_OBS_CACHE; /* table rows for dynamic cells; SF_OBS_TABLE_ROWS lowers it (tests of the path beyond the table) */
     long long launches = 0;
     std::string err;
 };
@@ -766,6 +603,10 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     h->d.n_envs = cfg->n_envs;
     h->d.E = (cfg->n_envs + 31) / 32 * 32;
     h->d.cap_t = (h->k.cap_t + 7) / 8 * 8;
+    if (const char *v = getenv("SF_OBS_TABLE_ROWS")) {
+        int n = atoi(v);
+        if (n >= 0 && n < SF_OBS_CACHE) h->obs_rows = n;
+    }
     if (const char *v = getenv("SF_LANES_PER_WARP")) {
         const int n = atoi(v);
         if (n == 1 || n == 2 || n == 4 || n == 8 || n == 16 || n == 32) h->lanes_per_warp = n;
@@ -818,8 +659,8 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_step_kernel<SF_HALF_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
     SF_CREATE_CUDA(cudaFuncSetAttribute(sf_rng_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
-    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_OBS_SMEM));
-    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_observe_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_OBSW_SMEM));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_OBS_SMEM));
+    SF_CREATE_CUDA(cudaFuncSetAttribute(sf_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_OBS_SMEM));
     rc = sf_launch_reset(h, nullptr, h->d.n_envs, nullptr, nullptr, 0);
     if (rc == SF_OK) {
         cudaError_t e_ = cudaDeviceSynchronize();
@@ -967,6 +808,8 @@ int sf_synth_actions(sf_handle *h, uint8_t *actions, uint64_t t, const char *tab
 int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, void *stream)
 {
     if (!h || !obs) return h ? sf_fail(h, SF_ERR_ARG, "sf_observe: null buffer") : SF_ERR_ARG;
+    const bool nhwc = (phase & SF_OBS_NHWC) != 0;
+    phase &= ~SF_OBS_NHWC;
     if (phase != SF_OBS_P1 && phase != SF_OBS_P2) return sf_fail(h, SF_ERR_ARG, "sf_observe: phase must be SF_OBS_P1 or SF_OBS_P2");
     /* the kernel describes the arena as it stands; the phase says WHERE in the step the caller claims
        to be, and a claim that does not match the handle is an error: P2 is the point between
@@ -979,15 +822,13 @@ int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, voi
     if (nsel == 0) return sf_fail(h, SF_ERR_ARG, "sf_observe: empty agent mask");
     if (reinterpret_cast<uintptr_t>(obs) & 15u) return sf_fail(h, SF_ERR_ARG, "sf_observe: obs must be 16-byte aligned");
     int n_items = h->d.n_envs * nsel;
-#ifdef SF_OBS_WS
-    int grid = n_items < SF_OBSW_CTAS_PER_SM * h->n_sm ? n_items : SF_OBSW_CTAS_PER_SM * h->n_sm;
-    sf_observe_ws_kernel<<<grid, SF_OBSW_CTA, SF_OBSW_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
-                                                                                                nsel, n_items);
-#else
     int grid = n_items < SF_OBS_CTAS_PER_SM * h->n_sm ? n_items : SF_OBS_CTAS_PER_SM * h->n_sm;
-    sf_observe_kernel<<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
-                                                                                          nsel, n_items);
-#endif
+    if (nhwc)
+        sf_observe_kernel<true><<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
+                                                                                                    nsel, n_items, h->obs_rows);
+    else
+        sf_observe_kernel<false><<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
+                                                                                                     nsel, n_items, h->obs_rows);
     h->launches += 1;
     SF_CUDA(h, cudaGetLastError());
     return SF_OK;

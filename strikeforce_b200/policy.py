@@ -24,6 +24,23 @@ def _l1norm(x, size):
     return x * (size / (flat.abs().sum(dim=1) + 1e-8)).view(-1, *([1] * (x.dim() - 1)))
 
 
+def _gru_step(gru, x, h):
+    """One time step of a one-layer ``nn.GRU`` (Modules.hpp:88, 92 call it with a sequence of one) as two
+    matrix products over the batch and the gate arithmetic of torch's GRU (gates in the order r, z, n;
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)); h' = (1 - z) * n + z * h).  The module keeps its
+    parameters -- same names, same checkpoints -- but is not called: cuDNN's persistent-RNN kernel, which
+    nn.GRU dispatches to, takes 10 ms per call for a batch of 32,768 rows with sequence length 1 (61% of the
+    whole forward, profiles/r02_policy_forward.txt); this is 0.3 ms."""
+    gi = F.linear(x, gru.weight_ih_l0, gru.bias_ih_l0)
+    gh = F.linear(h, gru.weight_hh_l0, gru.bias_hh_l0)
+    i_r, i_z, i_n = gi.chunk(3, dim=1)
+    h_r, h_z, h_n = gh.chunk(3, dim=1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return n + z * (h - n)
+
+
 class ResB(nn.Module):
     """Modules.hpp:29-52"""
 
@@ -75,17 +92,17 @@ class Backbone(nn.Module):
 
     def forward(self, x, h0, h1, action_input):
         B, H = x.shape[0], self.hidden
-        feat = _l1norm(self.cnn(x), H)                      # [B, H, 1, 1]
-        out0, h0n = self.gru0(feat.view(1, B, H), h0.view(1, B, H))
-        out_seq = _l1norm(out0.view(B, H), H)
+        feat = _l1norm(self.cnn(x), H).reshape(B, H)        # [B, H, 1, 1] -> [B, H]
+        h0n = _gru_step(self.gru0, feat, h0)                # a sequence of one: the output IS the new state
+        out_seq = _l1norm(h0n, H)
         c = self.grid // 2                                   # the five cells around the agent, :115-121
         cells = [(-1, 0), (0, -1), (0, 0), (0, 1), (1, 0)]
         pov = torch.cat([x[:, :, c + dr, c + dc] for dr, dc in cells] + [action_input], dim=1)
-        combined = torch.cat([out_seq + feat.view(B, H), _l1norm(pov, H)], dim=1)
+        combined = torch.cat([out_seq + feat, _l1norm(pov, H)], dim=1)
         gated = _l1norm(self.combined_processor(combined), H)
-        out1, h1n = self.gru1(gated.view(1, B, H), h1.view(1, B, H))
-        out = _l1norm(out1.view(B, H), H) + gated
-        return out, h0n.view(B, H), h1n.view(B, H)
+        h1n = _gru_step(self.gru1, gated, h1)
+        out = _l1norm(h1n, H) + gated
+        return out, h0n, h1n
 
 
 class AgentModel(nn.Module):
@@ -129,11 +146,16 @@ class PolicyAgent:
       (:204-208): action 0 gets probability 0.5 and the others are scaled by ``0.5 / (1 - p0 + 1e-5)``;
     * ``reset_rows(mask)`` is the new ``Agent`` of the next game (``reset_memory``, Modules.hpp:94-99):
       zero GRU states, the action one-hot back on index 0, the call counter back to 0 -- call it with
-      the arenas whose ``step_out`` status is terminal (``bots.play`` does)."""
+      the arenas whose ``step_out`` status is terminal (``bots.play`` does);
+    * ``channels_last=True`` keeps the convolution weights channel-innermost, to go with observations written
+      in that layout (``BatchedArena.observe(channels_last=True)``, ``bots.Custom(agent, channels_last=True)``):
+      same values, no transposes inside the convolution library (profiles/r02_policy_forward.txt)."""
 
     def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False, chunk=0, t_initial=10,
-                 slowmotion=True):
+                 slowmotion=True, channels_last=False):
         self.model = model.to(device).eval()
+        if channels_last:  # for observations written with SF_OBS_NHWC: the convolutions then run without a transpose
+            self.model = self.model.to(memory_format=torch.channels_last)
         self.state = model.initial_state(batch, device)
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed)

@@ -104,16 +104,25 @@ class BatchedArena:
         return out
 
     # ------------------------------------------------------------------ observation / readback
-    def observe(self, agent_mask=1, phase=sfcfg.OBS_P1, out=None):
+    def observe(self, agent_mask=1, phase=sfcfg.OBS_P1, out=None, channels_last=False):
         """gameplay::bot() up to Agent::predict (bots/bot-0.5/Custom.hpp:137-158): fp32 device
-        tensor [n_envs, n_selected, 32, 31, 31]."""
+        tensor [n_envs, n_selected, 32, 31, 31].
+
+        ``channels_last=True`` returns a tensor of the same shape and values whose MEMORY is
+        [n_envs, n_selected, 31, 31, 32] (SF_OBS_NHWC): ``.flatten(0, 1)`` of it is a channels-last batch that
+        the policy's first convolution reads without a transpose.  ``out`` is always the plain buffer in memory
+        order."""
         nsel = bin(agent_mask).count("1")
+        W, CH = sfcfg.OBS_WIN, sfcfg.OBS_CH
         if out is None:
-            out = torch.empty((self.n_envs, nsel, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32,
-                              device=self.device)
+            out = torch.empty((self.n_envs, nsel, W, W, CH) if channels_last else (self.n_envs, nsel, CH, W, W),
+                              dtype=torch.float32, device=self.device)
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
         assert out.numel() == self.n_envs * nsel * sfcfg.OBS_LEN
-        self._chk(lib().sf_observe(self._h, C.c_void_p(out.data_ptr()), phase, agent_mask, self._stream()))
+        self._chk(lib().sf_observe(self._h, C.c_void_p(out.data_ptr()), phase | (sfcfg.OBS_NHWC if channels_last else 0),
+                                   agent_mask, self._stream()))
+        if channels_last:
+            return out.view(self.n_envs, nsel, W, W, CH).permute(0, 1, 4, 2, 3)
         return out
 
     def _get(self, field, shape, dtype):

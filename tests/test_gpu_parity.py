@@ -493,3 +493,75 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
         for sm in sims:
             sm.close()
         host.close(), listener.close()
+
+
+def test_observation_layouts_and_the_path_beyond_the_table(torch_cuda, arena_data, monkeypatch):
+    """sf_observe's two memory layouts hold the same values bit for bit ([32][31][31] as the reference builds it,
+    Custom.hpp:139, and SF_OBS_NHWC with the channel innermost), and so does a handle whose feature table has
+    room for 2 dynamic cells only (SF_OBS_TABLE_ROWS): every other dynamic cell of a window then takes the
+    describe-during-copy-out path that a full table reaches only in very crowded windows.  The plain layout
+    of the first arenas is checked against the oracle as everywhere else."""
+    from strikeforce_b200.sim import BatchedArena
+    torch = torch_cuda
+    n, mask = 96, 0b1011
+    kw = dict(mode="Squad", level=3, squad_agents=True, auto_reset=False)
+    sim = BatchedArena(n, **kw)
+    monkeypatch.setenv("SF_OBS_TABLE_ROWS", "2")
+    small = BatchedArena(n, **kw)
+    monkeypatch.delenv("SF_OBS_TABLE_ROWS")
+    oracles = common.make_oracles(arena_data, 6, sfcfg.MODE_SQUAD, 3, squad_agents=True)
+    try:
+        for t in range(120):
+            act = sim.synth_actions(t, sfcfg.ACTIONS28)
+            if t % 10 == 0:
+                a = sim.observe(mask)
+                views = [sim.observe(mask, channels_last=True), small.observe(mask), small.observe(mask, channels_last=True)]
+                assert views[0].shape == a.shape and not views[0].is_contiguous()
+                assert views[0].flatten(0, 1).is_contiguous(memory_format=torch.channels_last)
+                for v in views:
+                    assert torch.equal(a.view(torch.int32), v.contiguous().view(torch.int32)), "layouts differ at step %d" % t
+                a_h = a.cpu().numpy()
+                for e, o in enumerate(oracles):
+                    for j, slot in enumerate((0, 1, 3)):
+                        try:
+                            ref = o.observe(slot)
+                        except RuntimeError:
+                            continue
+                        assert (a_h[e, j].reshape(-1).view(np.uint32) == ref.view(np.uint32)).all()
+            sim.step(act)
+            small.step(act)
+            act_h = act.cpu().numpy()
+            for e, o in enumerate(oracles):
+                o.step(bytes(act_h[e]))
+    finally:
+        sim.close()
+        small.close()
+
+
+def test_a_handle_runs_on_its_own_device(torch_cuda, arena_data):
+    """A handle is bound to the device that was current in sf_create; every entry point switches to it and
+    puts the caller's device back (SfDeviceGuard).  Needs two GPUs; the single-GPU case checks that the
+    calls leave the current device alone."""
+    from strikeforce_b200.sim import BatchedArena
+    torch = torch_cuda
+    n_dev = torch.cuda.device_count()
+    torch.cuda.set_device(0)
+    sim = BatchedArena(64, mode="Solo", level=1, auto_reset=False)
+    oracles = common.make_oracles(arena_data, 64, sfcfg.MODE_SOLO, 1)
+    try:
+        other = 1 if n_dev > 1 else 0
+        torch.cuda.set_device(other)  # the caller moves on to another GPU; the handle stays where it is
+        for t in range(20):
+            act = sim.synth_actions(t, sfcfg.ACTIONS28)
+            sim.step(act)
+            assert torch.cuda.current_device() == other
+            act_h = act.cpu().numpy()
+            for e, o in enumerate(oracles):
+                o.step(bytes(act_h[e]))
+        h = sim.state_hash().cpu().numpy().view(np.uint64)
+        assert all(h[e] == np.uint64(o.state_hash()) for e, o in enumerate(oracles))
+        if n_dev < 2:
+            pytest.skip("one GPU: the cross-device half of this test did not run")
+    finally:
+        torch.cuda.set_device(0)
+        sim.close()

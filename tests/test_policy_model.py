@@ -82,6 +82,27 @@ def test_batched_forward_matches_the_reference_network():
             st = AgentModel.with_action(st, act)
 
 
+def test_gru_step_is_torch_gru_and_channels_last_is_the_same_network():
+    """The recurrent layers run as two matrix products and the gate formula instead of nn.GRU's sequence
+    kernel (policy._gru_step): same parameters, same result as the module.  The channel-innermost copy of
+    the network (observations written with SF_OBS_NHWC) gives the same probabilities and values."""
+    from strikeforce_b200 import policy
+    torch.manual_seed(3)
+    m = formula_model()
+    with torch.no_grad():
+        for g in (m.backbone.gru0, m.backbone.gru1):
+            x, h = torch.rand(7, 160) - 0.5, torch.rand(7, 160) - 0.5
+            _, hn = g(x.view(1, 7, 160), h.view(1, 7, 160))
+            assert (hn.view(7, 160) - policy._gru_step(g, x, h)).abs().max() < 1e-6
+        x = torch.cat([formula_obs(s) for s in range(4)])
+        st = m.initial_state(4)
+        p, v, _ = m(x, st)
+        buf = x.permute(0, 2, 3, 1).contiguous()  # the memory sf_observe writes with SF_OBS_NHWC
+        m2 = formula_model().to(memory_format=torch.channels_last)
+        p2, v2, _ = m2(buf.permute(0, 3, 1, 2), st)
+        assert (p - p2).abs().max() < TOL and (v - v2).abs().max() < TOL
+
+
 def test_policy_agent_is_seeded_and_batched():
     m = formula_model()
     a1, a2 = PolicyAgent(m, 4, device="cpu", seed=3, t_initial=0), PolicyAgent(m, 4, device="cpu", seed=3, t_initial=0)

@@ -252,7 +252,7 @@ __device__ __forceinline__ void sf_obs_item(int item, int nsel, uint32_t agent_m
 template <bool NHWC> /* NHWC: the same values with the channel innermost, SF_OBS_NHWC of the header */
 __global__ void __launch_bounds__(SF_OBS_CTA, SF_OBS_CTAS_PER_SM)
 sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__restrict__ obs, uint32_t agent_mask,
-                  int nsel, int n_items, int rows)
+                  int nsel, int n_items, int rows, int run_len)
 {
     float *feat = reinterpret_cast<float *>(sf_smem);                         /* [row][SF_OBS_PITCH] */
     uint16_t *code = reinterpret_cast<uint16_t *>(feat + SF_OBS_ROWS * SF_OBS_PITCH); /* per window cell */
@@ -272,7 +272,8 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
         for (int c = 0; c < SF_OBS_CH; ++c) feat[threadIdx.x * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
     }
     constexpr int PER = (SF_OBS_CELLS + SF_OBS_CTA - 1) / SF_OBS_CTA;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int run = blockIdx.x; run * run_len < n_items; run += gridDim.x)
+    for (int item = run * run_len, end = min(n_items, item + run_len); item < end; ++item) {
         int env, slot;
         sf_obs_item(item, nsel, agent_mask, &env, &slot);
         float *out = obs + (size_t)item * SF_OBS_LEN;
@@ -352,10 +353,13 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
             for (int c = 0; c < SF_OBS_CH; ++c) feat[(16 + i) * SF_OBS_PITCH + c] = f[c] ? sf_obs_transform(d, f[c], &fb) : 0.f;
         }
         __syncthreads();
-        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM; every store
-           instruction of a warp covers 512 contiguous bytes.  Measured and rejected: storing the all-zero
-           chunks first and the others in a second pass, lane-dense (41% slower: partial-warp stores); a
-           warp vote that sends 128 empty cells in a row down a store-only path (7% slower) */
+        /* the copy-out: no barrier, no shared-memory buffer between the table and HBM; every store instruction
+           of a warp covers 512 contiguous bytes.  What HBM makes of a pure store stream depends on its shape
+           (tools/gpu_write_peak.py, profiles/r02_write_peak.txt): a plain store kernel in which every CTA writes
+           one 123 KB observation front to back and then moves on reaches 5.1 TB/s, 6.1 TB/s when a CTA writes
+           four or more consecutive observations (hence run_len).  Measured and rejected: storing the all-zero
+           chunks first and the others in a second pass, lane-dense (41% slower: partial-warp stores); a warp
+           vote that sends 128 empty cells in a row down a store-only path (7% slower) */
         float4 *dst = reinterpret_cast<float4 *>(out);
         if constexpr (NHWC) {
             /* channel-innermost: the 32 features of a cell are one table row = eight chunks; chunk idx
@@ -381,45 +385,58 @@ sf_observe_kernel(const SfDev d, const __grid_constant__ SfConst k, float *__res
                 }
                 __stcs(dst + idx, v);
             }
-        } else
-        for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
-            int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
-            int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
-            bool beyond = false;
+        } else {
+            /* [32][31][31]: 961 = 1 (mod 4), so every four channels are exactly 961 chunks and chunk q covers
+               the same (channel offset, cell) quadruple in each of the eight 4-channel groups; a thread reads
+               the four codes of its chunk once and then writes the chunk of every group: four predicated table
+               reads (the group is an immediate) and one 16-byte store each.  The price is alignment: the warp
+               stores of group g start 16 g bytes off a 512-byte boundary, and a plain store kernel shows what
+               HBM makes of that (tools/gpu_write_peak.py: 6.1 TB/s aligned, 5.75 TB/s on any other 32-byte
+               boundary, 4.4 TB/s from the middle of a 32-byte sector).  Measured and rejected
+               (profiles/r02_variants.txt): a walk with every warp store on a 512-byte boundary (chunk
+               g * 960 + r, the codes packed once per window into one word per chunk) has to unpack and
+               address the four codes per chunk AND per group -- twice the instructions of this loop,
+               3.76 ms; this loop with a thread owning chunk q of the even groups and q - 1 of the odd ones
+               (every warp store then starts on a sector boundary) decodes twice, 3.89 ms. */
+            for (int q = threadIdx.x; q < SF_OBS_GROUP; q += SF_OBS_CTA) {
+                int cc = (4 * q) / SF_OBS_CELLS, w = 4 * q - cc * SF_OBS_CELLS; /* channel offset in the group, window cell */
+                int row[4];  /* table offset of element j of the chunk: row * pitch + channel offset, -1 = zero */
+                bool beyond = false;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t cd = code[w];
-                row[j] = cd ? (int)cd * SF_OBS_PITCH + cc : -1;
-                if (cd == SF_OBS_BEYOND) beyond = true, row[j] = -2 - w;
-                if (++w == SF_OBS_CELLS) w = 0, ++cc;
-            }
-            if (!beyond) {
-#pragma unroll
-                for (int g = 0; g < SF_OBS_CH / 4; ++g) {
-                    float4 v;
-                    v.x = row[0] >= 0 ? feat[row[0] + 4 * g] : 0.f;
-                    v.y = row[1] >= 0 ? feat[row[1] + 4 * g] : 0.f;
-                    v.z = row[2] >= 0 ? feat[row[2] + 4 * g] : 0.f;
-                    v.w = row[3] >= 0 ? feat[row[3] + 4 * g] : 0.f;
-                    __stcs(dst + g * SF_OBS_GROUP + q, v);
-                }
-            } else { /* more dynamic cells than table rows (rare): those are described here, once per chunk */
-                float val[4][SF_OBS_CH / 4];
-                int cj = (4 * q) / SF_OBS_CELLS, wj = 4 * q - cj * SF_OBS_CELLS;
-#pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
-                    if (row[j] <= -2) {
-                        const int cell = sf_obs_cell(vcell, wj / SF_OBS_WIN, wj % SF_OBS_WIN);
-                        int32_t f[32];
-                        sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[wj], tmap[wj], f);
-                        for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = f[4 * g + cj] ? sf_obs_transform(d, f[4 * g + cj], &fb) : 0.f;
-                    } else {
-                        for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = row[j] >= 0 ? feat[row[j] + 4 * g] : 0.f;
-                    }
-                    if (++wj == SF_OBS_CELLS) wj = 0, ++cj;
+                    const uint32_t cd = code[w];
+                    row[j] = cd ? (int)cd * SF_OBS_PITCH + cc : -1;
+                    if (cd == SF_OBS_BEYOND) beyond = true, row[j] = -2 - w;
+                    if (++w == SF_OBS_CELLS) w = 0, ++cc;
                 }
-                for (int g = 0; g < SF_OBS_CH / 4; ++g)
-                    __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
+                if (!beyond) {
+#pragma unroll
+                    for (int g = 0; g < SF_OBS_CH / 4; ++g) {
+                        float4 v;
+                        v.x = row[0] >= 0 ? feat[row[0] + 4 * g] : 0.f;
+                        v.y = row[1] >= 0 ? feat[row[1] + 4 * g] : 0.f;
+                        v.z = row[2] >= 0 ? feat[row[2] + 4 * g] : 0.f;
+                        v.w = row[3] >= 0 ? feat[row[3] + 4 * g] : 0.f;
+                        __stcs(dst + g * SF_OBS_GROUP + q, v);
+                    }
+                } else { /* more dynamic cells than table rows (rare): those are described here, once per chunk */
+                    float val[4][SF_OBS_CH / 4];
+                    int cj = (4 * q) / SF_OBS_CELLS, wj = 4 * q - cj * SF_OBS_CELLS;
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        if (row[j] <= -2) {
+                            const int cell = sf_obs_cell(vcell, wj / SF_OBS_WIN, wj % SF_OBS_WIN);
+                            int32_t f[32];
+                            sf_describe_cell(d, k, env, e, cell, t.smap[cell], SF_G(cell), team, bmap[wj], tmap[wj], f);
+                            for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = f[4 * g + cj] ? sf_obs_transform(d, f[4 * g + cj], &fb) : 0.f;
+                        } else {
+                            for (int g = 0; g < SF_OBS_CH / 4; ++g) val[j][g] = row[j] >= 0 ? feat[row[j] + 4 * g] : 0.f;
+                        }
+                        if (++wj == SF_OBS_CELLS) wj = 0, ++cj;
+                    }
+                    for (int g = 0; g < SF_OBS_CH / 4; ++g)
+                        __stcs(dst + g * SF_OBS_GROUP + q, make_float4(val[0][g], val[1][g], val[2][g], val[3][g]));
+                }
             }
         }
     }
@@ -472,6 +489,8 @@ struct sf_handle {
     int device = 0, n_sm = 0;
     bool between_halves = false; /* sf_step_a has run, sf_step_b has not: the P2 observation point */
     int lanes_per_warp = 0;      /* 0 = chosen from the batch size; SF_LANES_PER_WARP overrides (measurements) */
+    int obs_run = 0;             /* consecutive observations a CTA writes before it moves on; 0 = chosen from the
+                                    batch size, SF_OBS_RUN overrides (measurements) */
     int obs_rows = SF_OBS_CACHE; /* table rows for dynamic cells; SF_OBS_TABLE_ROWS lowers it (tests of the path beyond the table) */
     long long launches = 0;
     std::string err;
@@ -603,6 +622,10 @@ int sf_create(const sf_config *cfg, sf_handle **out)
     h->d.n_envs = cfg->n_envs;
     h->d.E = (cfg->n_envs + 31) / 32 * 32;
     h->d.cap_t = (h->k.cap_t + 7) / 8 * 8;
+    if (const char *v = getenv("SF_OBS_RUN")) {
+        int n = atoi(v);
+        if (n >= 1 && n <= 4096) h->obs_run = n;
+    }
     if (const char *v = getenv("SF_OBS_TABLE_ROWS")) {
         int n = atoi(v);
         if (n >= 0 && n < SF_OBS_CACHE) h->obs_rows = n;
@@ -822,13 +845,21 @@ int sf_observe(sf_handle *h, float *obs, int32_t phase, uint32_t agent_mask, voi
     if (nsel == 0) return sf_fail(h, SF_ERR_ARG, "sf_observe: empty agent mask");
     if (reinterpret_cast<uintptr_t>(obs) & 15u) return sf_fail(h, SF_ERR_ARG, "sf_observe: obs must be 16-byte aligned");
     int n_items = h->d.n_envs * nsel;
-    int grid = n_items < SF_OBS_CTAS_PER_SM * h->n_sm ? n_items : SF_OBS_CTAS_PER_SM * h->n_sm;
+    /* a CTA writes runs of consecutive observations: HBM takes 1,184 store streams that each run on for
+       megabytes better than a front of 123 KB pieces (profiles/r02_obs_run.txt: 73 -> 80% of the peak); the
+       longest run of up to 16 that still leaves every CTA four turns */
+    const int ctas = SF_OBS_CTAS_PER_SM * h->n_sm;
+    int run_len = h->obs_run;
+    if (run_len == 0)
+        for (run_len = 16; run_len > 1 && n_items / run_len < 4 * ctas; run_len >>= 1) {}
+    int runs = (n_items + run_len - 1) / run_len;
+    int grid = runs < ctas ? runs : ctas;
     if (nhwc)
         sf_observe_kernel<true><<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
-                                                                                                    nsel, n_items, h->obs_rows);
+                                                                                                    nsel, n_items, h->obs_rows, run_len);
     else
         sf_observe_kernel<false><<<grid, SF_OBS_CTA, SF_OBS_SMEM, static_cast<cudaStream_t>(stream)>>>(h->d, h->k, obs, agent_mask,
-                                                                                                     nsel, n_items, h->obs_rows);
+                                                                                                     nsel, n_items, h->obs_rows, run_len);
     h->launches += 1;
     SF_CUDA(h, cudaGetLastError());
     return SF_OK;

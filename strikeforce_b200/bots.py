@@ -65,10 +65,17 @@ class Custom:
 
     action = sfcfg.ACTIONS9  # gameplay::action = "+xzqeawsd", Custom.hpp:162
 
-    def __init__(self, agent: Agent | None = None, channels_last=False):
+    def __init__(self, agent: Agent | None = None, channels_last=None):
         self.agent = agent
-        self.channels_last = channels_last  # the layout sf_observe writes (SF_OBS_NHWC); shape and values are the same
+        # the layout sf_observe writes (SF_OBS_NHWC; shape and values are the same): None = what the agent asks for
+        self._channels_last = channels_last
         self._table = None
+
+    @property
+    def channels_last(self):
+        if self._channels_last is not None:
+            return self._channels_last
+        return bool(getattr(self.agent, "channels_last", False))
 
     def prepare(self, sim):
         if self.agent is None:

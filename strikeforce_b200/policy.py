@@ -147,13 +147,15 @@ class PolicyAgent:
     * ``reset_rows(mask)`` is the new ``Agent`` of the next game (``reset_memory``, Modules.hpp:94-99):
       zero GRU states, the action one-hot back on index 0, the call counter back to 0 -- call it with
       the arenas whose ``step_out`` status is terminal (``bots.play`` does);
-    * ``channels_last=True`` keeps the convolution weights channel-innermost, to go with observations written
-      in that layout (``BatchedArena.observe(channels_last=True)``, ``bots.Custom(agent, channels_last=True)``):
-      same values, no transposes inside the convolution library (profiles/r02_policy_forward.txt)."""
+    * ``channels_last=True`` (the default) keeps the convolution weights channel-innermost, to go with
+      observations written in that layout (``BatchedArena.observe(channels_last=True)``; ``bots.Custom`` asks for
+      the layout its agent wants): same values, no transposes inside the convolution library
+      (profiles/r02_policy_forward.txt).  Observations in the reference's [32][31][31] order are accepted either way."""
 
     def __init__(self, model: AgentModel, batch, device="cuda", seed=0, training=False, chunk=0, t_initial=10,
-                 slowmotion=True, channels_last=False):
+                 slowmotion=True, channels_last=True):
         self.model = model.to(device).eval()
+        self.channels_last = channels_last  # bots.Custom asks sf_observe for the matching layout
         if channels_last:  # for observations written with SF_OBS_NHWC: the convolutions then run without a transpose
             self.model = self.model.to(memory_format=torch.channels_last)
         self.state = model.initial_state(batch, device)

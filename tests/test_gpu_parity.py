@@ -528,8 +528,18 @@ def test_observation_layouts_and_the_path_beyond_the_table(torch_cuda, arena_dat
                         except RuntimeError:
                             continue
                         assert (a_h[e, j].reshape(-1).view(np.uint32) == ref.view(np.uint32)).all()
-            sim.step(act)
-            small.step(act)
+            if t % 20 == 10:  # the P2 observation point, between the two halves of the step, in both layouts
+                sim.step_a()
+                small.step_a()
+                p2 = sim.observe(mask & ~1, sfcfg.OBS_P2)
+                for v in (sim.observe(mask & ~1, sfcfg.OBS_P2, channels_last=True), small.observe(mask & ~1, sfcfg.OBS_P2),
+                          small.observe(mask & ~1, sfcfg.OBS_P2, channels_last=True)):
+                    assert torch.equal(p2.view(torch.int32), v.contiguous().view(torch.int32)), "P2 layouts differ at step %d" % t
+                sim.step_b(act)
+                small.step_b(act)
+            else:
+                sim.step(act)
+                small.step(act)
             act_h = act.cpu().numpy()
             for e, o in enumerate(oracles):
                 o.step(bytes(act_h[e]))

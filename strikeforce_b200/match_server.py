@@ -29,6 +29,7 @@ that never attack, and 1,500 ticks of the whole alphabet, where the rules that d
 it is come into play (kill and loot credits, the own corpse keeping its cell, gameplay.hpp:591-592,
 629-630, 642-645).  Scripted socket clients check the bytes of quits, eliminations and the winner,
 that a client which goes silent is dropped after the time-out instead of freezing the match, and a
+GPU-hosted match plays its own seat with a device agent observing that seat's arena (tests/test_gpu_parity.py), and a
 match between two live reference clients is left alone until it is over (a player falls, its client
 reports '~', result() names the winner) with every copy equal to the host's arena of its seat to the end.
 """

@@ -430,12 +430,15 @@ def test_policy_loop_stays_on_the_device(torch_cuda, arena_data):
             sim.close()
 
 
-def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
+@pytest.mark.parametrize("seat_player", ["scripted", "device-agent"])
+def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data, seat_player):
     """a match hosted with the reference server's wire protocol
     (strikeforce_b200.match_server) whose arenas live on the GPU -- one per SEAT (sf_config.royale_ind):
     the copy of the match each seat's own client holds, kill credits and corpses included; two scripted
     socket clients and one host-played seat, every seat's arena compared with the oracle of that seat fed
-    the relayed commands."""
+    the relayed commands.  The host's own seat is played from a script or by a DEVICE AGENT: the seat's arena
+    is observed from that player's position (sf_observe on the arena whose ind is the seat), the batched
+    AgentModel picks the command, and the host sends it to the other clients like any player's byte."""
     import socket
     import threading
     import test_match_server as tms
@@ -479,12 +482,29 @@ def test_match_host_steps_a_gpu_arena(torch_cuda, arena_data):
                 oa.step(row)
                 assert np.uint64(sm.state_hash().cpu().numpy().view(np.uint64)[0]) == np.uint64(oa.state_hash())
 
+        agent = None
+        if seat_player == "device-agent":
+            from strikeforce_b200 import policy as sfpolicy
+            torch.manual_seed(5)
+            agent = sfpolicy.PolicyAgent(sfpolicy.AgentModel(), 1, device=sims[1].device, seed=9, t_initial=2)
+        played = []
+
         def policy(seat):
             tick[0] += 1
-            return int(acts[tick[0] - 1, 1])
+            if agent is None:
+                return int(acts[tick[0] - 1, 1])
+            obs = sims[seat].observe(1 << seat, channels_last=agent.channels_last)  # what this seat's own client would see
+            cmd = int(sfcfg.ACTIONS9[int(agent.predict(obs.flatten(0, 1))[0])])
+            played.append(cmd)
+            return cmd
 
         winner, ticks = ms.host_match(host, step, policy, max_ticks=T)
         assert ticks == T and winner == 0
+        if agent is not None:
+            assert len(played) == T and played[:2] == [ord("+")] * 2 and all(c in sfcfg.ACTIONS9 for c in played)
+            for c, pos in zip(clients, (0, 1)):  # the agent's commands reached seats 0 and 2 as the bytes of player 1
+                c.join(10)
+                assert [r[pos] for r in c.received] == played
         assert np.uint64(sim.state_hash()[0].item() & 0xFFFFFFFFFFFFFFFF) == np.uint64(o.state_hash())
         for c in clients:
             c.join(10)

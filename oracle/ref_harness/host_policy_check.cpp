@@ -6,7 +6,7 @@
 // (strikeforce_b200.bots / policy) and compares.  TEST INFRASTRUCTURE: includes the reference's
 // header, so it is built into oracle/_ref/ by build_host_check.sh and never shipped.
 //
-//   host_policy_check <config blob> <ticks> <out file>
+//   host_policy_check <config blob> <ticks> <out file> [nhwc]     (nhwc: observations written channel-innermost)
 #include "bots/bot-0.5/Modules.hpp"
 
 #include <cstdio>
@@ -78,7 +78,8 @@ int main(int argc, char **argv)
         auto dev = torch::Device(torch::kCUDA, 0);
         auto policy = std::make_shared<ReferencePolicy>(c.cfg.n_envs, dev);
         auto agent = std::make_shared<sfb200::Agent>(policy, false, /*greedy=*/true);
-        sfb200::BatchedGameplay g(c.cfg, agent);
+        const bool nhwc = argc > 4 && std::string(argv[4]) == "nhwc";
+        sfb200::BatchedGameplay g(c.cfg, agent, "+xzqeawsd", nhwc);
         std::ofstream f(argv[3], std::ios::binary);
         for (int t = 0; t < ticks; ++t) {
             g.tick();

@@ -66,7 +66,10 @@ def test_cpp_host_plays_like_the_python_mirror(arena_data, tmp_path):
 
 
 @pytest.mark.gpu
-def test_reference_network_drives_the_binding(arena_data, tmp_path):
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_reference_network_drives_the_binding(arena_data, tmp_path, layout):
+    """... `nhwc`: the binding asks sf_observe for channel-innermost observations (SF_OBS_NHWC) and hands the
+    reference's network the same [B,32,31,31] tensor with channels-last strides: same commands, same arenas."""
     import torch
     if not os.path.exists(CHECK):
         pytest.skip("oracle/_ref/host_policy_check is built where the reference tree is (oracle/ref_harness/build_host_check.sh)")
@@ -80,7 +83,8 @@ def test_reference_network_drives_the_binding(arena_data, tmp_path):
     cfg = sfcfg.make_config(arena_data, n_envs=n, mode=sfcfg.MODE_SOLO, level_min=1, level_max=3, auto_reset=False, env_id_base=40)
     blob, res = tmp_path / "cfg.bin", tmp_path / "res.bin"
     sfcfg.dump_config(cfg, str(blob))
-    out = subprocess.run([CHECK, str(blob), str(ticks), str(res)], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([CHECK, str(blob), str(ticks), str(res)] + (["nhwc"] if layout == "nhwc" else []),
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     raw = res.read_bytes()
     per = n * 9 * 4 + n + n * 8

@@ -414,10 +414,12 @@ def run_royale(args):
     torch.cuda.set_device(local)
     # the reference network is fp32 (libtorch on the CPU); here the linear layers and GRUs stay fp32 and the
     # convolutions run as cuDNN runs them by default on this GPU (TF32 tensor-core math, fp32 accumulate):
-    # strict fp32 convolutions are 8x slower (4.4 s per tick, profiles/) and the policy is sampled anyway.
+    # strict fp32 convolutions (--strict-fp32) cost 1.04 s per tick instead of 0.107 s (profiles/) and the policy
+    # is sampled anyway.
     # The parity tests of the network (tests/test_policy_model.py, test_cpp_host.py) run with TF32 off.
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = not args.strict_fp32
+    torch.backends.cudnn.benchmark = True  # no effect on the TF32 path; 4x on strict fp32 (cuDNN's default pick is poor there)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E = args.envs if args.envs != WORKLOAD["envs_per_gpu"] else ROYALE["envs_per_gpu"]
@@ -459,7 +461,8 @@ def run_royale(args):
     ms_step = timed(lambda: sim.step(acts[next(it) % len(acts)]), 4 * K, W)
     # the observations are written channel-innermost (SF_OBS_NHWC: same values, [31][31][32] per observation) so
     # that the first convolution reads them as they are; --nchw keeps the reference's [32][31][31]
-    cl = not args.nchw
+    # (--strict-fp32 keeps the reference's layout: that is the combination that was measured)
+    cl = not args.nchw and not args.strict_fp32
     obs = torch.empty((E, P, sfcfg.OBS_WIN, sfcfg.OBS_WIN, sfcfg.OBS_CH) if cl else
                       (E, P, sfcfg.OBS_CH, sfcfg.OBS_WIN, sfcfg.OBS_WIN), dtype=torch.float32, device=sim.device)
     mask = (1 << P) - 1

@@ -71,9 +71,21 @@ extern "C" __global__ void __launch_bounds__(128, 8) fillg(float4 *dst, size_t n
                 for (int q = threadIdx.x; q < 961; q += 128) __stcs(d + g * 961 + q, make_float4(0.f, 0.f, 0.f, 0.f));
         }
 }
+extern "C" __global__ void __launch_bounds__(128, 8) fill32(float *dst, size_t n_units, size_t per_cta)
+{   /* the same walk with 32-byte stores (st.global.v8, sm_100): 1 KB per warp instruction */
+    for (size_t blk = blockIdx.x; blk * per_cta < n_units; blk += gridDim.x) {
+        float *d = dst + blk * per_cta * 8;
+        for (size_t q = threadIdx.x; q < per_cta; q += 128)
+            asm volatile("st.global.cs.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "l"(d + q * 8), "f"(0.f) : "memory");
+    }
+}
 extern "C" void launch(void *dst, size_t n_chunks, size_t per_cta, int grid, void *stream)
 {
     fill<<<grid, 128, 0, (cudaStream_t)stream>>>((float4 *)dst, n_chunks, per_cta);
+}
+extern "C" void launch32(void *dst, size_t n_units, size_t per_cta, int grid, void *stream)
+{
+    fill32<<<grid, 128, 0, (cudaStream_t)stream>>>((float *)dst, n_units, per_cta);
 }
 extern "C" void launchg(void *dst, size_t n_obs, int run, int grid, void *stream)
 {
@@ -107,6 +119,11 @@ with tempfile.TemporaryDirectory() as td:
         print("store kernel, front to back by groups (misaligned warp stores), runs of %2d: %.3f ms = %.0f GB/s written" % (run, ms, n_obs * 123008 / ms / 1e6))
         ms = timed(lambda: k.launch(a.data_ptr(), n_obs * 7688, 7688 * run, 8 * sms, torch.cuda.current_stream().cuda_stream))
         print("store kernel, front-to-back order, runs of %2d observations: %.3f ms = %.0f GB/s written" % (run, ms, n_obs * 123008 / ms / 1e6))
+    k.launch32.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    for run in (1, 16):
+        ms = timed(lambda: k.launch32(a.data_ptr(), n_obs * 3844, 3844 * run, 8 * sms, torch.cuda.current_stream().cuda_stream))
+        print("store kernel, front to back, 32-byte stores (st.global.v8), runs of %2d observations: %.3f ms = %.0f GB/s written"
+              % (run, ms, n_obs * 123008 / ms / 1e6))
     # the same front-to-back walk with every warp store starting `shift` chunks (16 bytes each) off a 512-byte boundary
     for shift in (0, 1, 2, 3, 4, 8, 16):
         ms = timed(lambda: k.launch(a.data_ptr() + 16 * shift, n_obs * 7688 - 32, 7688 * 16, 8 * sms, torch.cuda.current_stream().cuda_stream))

@@ -43,6 +43,21 @@ def test_no_cpu_fallback(arena_data):
     assert "oracle" not in src and "hostcheck" not in src, "the product must not reach into the test models"
 
 
+def test_python_mirror_of_the_header_constants():
+    """The Python mirror (strikeforce_b200/config.py) carries the header's values."""
+    hdr = open(os.path.join(ROOT, "include", "strikeforce_b200.h")).read()
+
+    def const(name):
+        m = re.search(r"\b%s\s*=?\s*(0x[0-9A-Fa-f]+|-?\d+)" % name, hdr)
+        assert m, name + " not found in the header"
+        return int(m.group(1), 0)
+
+    assert const("SF_ABI_VERSION") == sfcfg.ABI_VERSION
+    assert (const("SF_OBS_P1"), const("SF_OBS_P2"), const("SF_OBS_NHWC")) == (sfcfg.OBS_P1, sfcfg.OBS_P2, sfcfg.OBS_NHWC)
+    assert sfcfg.OBS_NHWC & (sfcfg.OBS_P1 | sfcfg.OBS_P2) == 0  # a flag or-ed into the phase
+    assert (const("SF_OBS_CH"), const("SF_OBS_WIN")) == (sfcfg.OBS_CH, sfcfg.OBS_WIN)
+
+
 def test_struct_layout_matches_header():
     assert C.sizeof(sfcfg.StepOut) == 32
     assert sfcfg.SfConfig.map_cells.offset % 8 == 0

@@ -499,7 +499,10 @@ def run_royale(args):
             "metric": METRIC, "value": world * E / (ms_tick / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_tick, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (tick), fp32 policy" + ("" if args.strict_fp32 else " with TF32 convolutions (cuDNN default)"),
             "data": "synthetic (seeded matches, random-init policy weights)",
-            "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P, observation_layout="nhwc" if cl else "nchw"),
+            "config": dict(ROYALE, envs_per_gpu=E, agents_per_env=P, observation_layout="nhwc" if cl else "nchw",
+                           **({"mode": ROYALE["mode"].replace("the reference's 3x30x100 map", "a larger map, 3x%dx%d: the reference's embedded in open "
+                                                              "ground (SF_GEOMETRY; parity there is pinned against the C oracle only)"
+                                                              % (sfcfg.ROWS, sfcfg.COLS))} if sfcfg.GEOMETRY_TAG else {})),
             "setup": {"prewarm_steps": min(args.prewarm, 512),
                       "mean_population": dict(zip(["humans", "zombies", "bullets", "chests", "built", "portals"], [round(x, 2) for x in pop]))},
             "e2e": {"value": world * E / (ms_play / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 128 // max(1, K),

@@ -28,10 +28,18 @@ extern "C" {
 
 #define SF_ABI_VERSION 3
 
-/* arena geometry of the reference (gameplay.hpp:37: F = 3, N = 30, M = 100) */
+/* arena geometry: compile-time constants, as in the reference (gameplay.hpp:37: F = 3, N = 30, M = 100).
+   A library for a larger map is the same source built with -DSF_ROWS= -DSF_COLS= (csrc/build.sh with
+   SF_GEOMETRY=40x128 builds libstrikeforce_b200_40x128.so); rows x columns, rounded up to tiles of 4 x 8, must
+   keep a cell id within 14 bits: 3 * ceil(rows / 4) * ceil(cols / 8) * 32 <= 16,384.  sf_config.map_cells /
+   map_portal are [SF_CELLS] of the library they are handed to. */
 #define SF_FLOORS 3
+#ifndef SF_ROWS
 #define SF_ROWS   30
+#endif
+#ifndef SF_COLS
 #define SF_COLS   100
+#endif
 #define SF_CELLS  (SF_FLOORS * SF_ROWS * SF_COLS)
 
 #define SF_OBS_CH   32                                   /* bots/bot-0.5/Custom.hpp:29-135 */

@@ -15,12 +15,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 from strikeforce_b200 import config as sfcfg  # noqa: E402  (struct layouts only)
 
-LIB_PATH = os.path.join(HERE, "libsforacle.so")
+LIB_PATH = os.path.join(HERE, "libsforacle%s.so" % sfcfg.GEOMETRY_TAG)
 OBS_LEN = sfcfg.OBS_LEN
 _lib = None
 
 
 def build():
+    if sfcfg.GEOMETRY_TAG:  # the same source for a larger arena (SF_GEOMETRY): dimensions are compile-time constants
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter",
+                               "-I" + os.path.join(ROOT, "include")] + sfcfg.GEOMETRY_CFLAGS +
+                              ["-shared", os.path.join(HERE, "sf_oracle.c"), "-o", LIB_PATH, "-lm"])
+        return
     subprocess.check_call(["make", "-s", "-C", HERE, "libsforacle.so"])
 
 

@@ -15,8 +15,10 @@ import numpy as np
 from . import data as sfdata
 
 ABI_VERSION = 3
-FLOORS, ROWS, COLS = 3, 30, 100  # SF_FLOORS / SF_ROWS / SF_COLS (gameplay.hpp:37)
+# SF_FLOORS / SF_ROWS / SF_COLS (gameplay.hpp:37); SF_GEOMETRY in the environment selects a larger arena (data.py)
+FLOORS, ROWS, COLS = sfdata.FLOORS, sfdata.ROWS, sfdata.COLS
 CELLS = FLOORS * ROWS * COLS
+GEOMETRY_TAG, GEOMETRY_CFLAGS = sfdata.GEOMETRY_TAG, sfdata.GEOMETRY_CFLAGS
 OBS_CH, OBS_WIN = 32, 31
 OBS_LEN = OBS_CH * OBS_WIN * OBS_WIN
 SHEET_LEN = sfdata.SHEET_LEN

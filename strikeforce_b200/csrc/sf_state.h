@@ -41,9 +41,12 @@
  * four neighbours of a cell usually lie in the same granule (a row-major grid needs three).
  * id = tile << 5 | (row & 3) << 3 | (col & 7), tile = (floor * 8 + row / 4) * 13 + col / 8.
  * Cells of the padding rows 30, 31 and columns 100..103 are never referenced. */
-#define SF_TILES_X 13
-#define SF_TILES_Y 8
+#define SF_TILES_X ((SF_COLS + 7) / 8) /* 13 */
+#define SF_TILES_Y ((SF_ROWS + 3) / 4) /* 8 */
 #define SF_TCELLS (SF_FLOORS * SF_TILES_Y * SF_TILES_X * 32) /* 9,984 */
+#if SF_TCELLS > 16384
+#error "cell ids are 14 bits wide (position words, sf_state.h): 3 * ceil(rows/4) * ceil(cols/8) * 32 must not exceed 16,384"
+#endif
 #define SF_GRID_STRIDE SF_TCELLS
 
 #ifdef __CUDACC__
@@ -58,8 +61,8 @@ SF_HDI int sf_tcell(int f, int r, int c)
 SF_HDI void sf_tcell_decode(int t, int *f, int *r, int *c)
 {
     int tile = t >> 5, trow = tile / SF_TILES_X, tcol = tile - trow * SF_TILES_X;
-    *f = trow >> 3;
-    *r = ((trow & 7) << 2) | ((t >> 3) & 3);
+    *f = trow / SF_TILES_Y;
+    *r = ((trow % SF_TILES_Y) << 2) | ((t >> 3) & 3);
     *c = (tcol << 3) | (t & 7);
 }
 

@@ -21,7 +21,17 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-FLOORS, ROWS, COLS = 3, 30, 100
+# The arena's dimensions are compile-time constants of the library, as they are in the reference
+# (gameplay.hpp:37: 3 x 30 x 100).  SF_GEOMETRY=ROWSxCOLS in the environment selects a library built for a
+# larger arena (csrc/build.sh) and makes load_default() embed the reference's map in one of that size.
+REF_ROWS, REF_COLS = 30, 100
+_geo = os.environ.get("SF_GEOMETRY", "")
+FLOORS = 3
+ROWS, COLS = (int(_geo.split("x")[0]), int(_geo.split("x")[1])) if _geo else (REF_ROWS, REF_COLS)
+assert ROWS >= REF_ROWS and COLS >= REF_COLS and FLOORS * ((ROWS + 3) // 4) * ((COLS + 7) // 8) * 32 <= 16384, \
+    "SF_GEOMETRY: at least 30x100, and cell ids must fit 14 bits"
+GEOMETRY_TAG = "" if (ROWS, COLS) == (REF_ROWS, REF_COLS) else "_%dx%d" % (ROWS, COLS)
+GEOMETRY_CFLAGS = ["-DSF_ROWS=%d" % ROWS, "-DSF_COLS=%d" % COLS] if GEOMETRY_TAG else []
 CELLS = FLOORS * ROWS * COLS
 SHEET_LEN = 32
 
@@ -163,12 +173,40 @@ def to_json(data: ArenaData):
     }
 
 
+def enlarge(cells, portal):
+    """The reference's 3 x 30 x 100 map as the top-left part of a ROWS x COLS one (a "large custom map",
+    BASELINE.json configs[4]): the rest is open floor inside a closed border, reached through doors cut into the
+    reference map's own bottom and right walls.  The static exits keep their scan order, so every '^' / 'v'
+    still leads where it led."""
+    big = np.full((FLOORS, ROWS, COLS), ord("."), dtype=np.uint8)
+    bigp = np.full((FLOORS, ROWS, COLS), -1, dtype=np.int16)
+    big[:, :REF_ROWS, :REF_COLS] = cells.reshape(FLOORS, REF_ROWS, REF_COLS)
+    bigp[:, :REF_ROWS, :REF_COLS] = portal.reshape(FLOORS, REF_ROWS, REF_COLS)
+    wall = ord("#")
+    if ROWS > REF_ROWS:
+        for c in range(5, REF_COLS - 1, 10):
+            door = big[:, REF_ROWS - 1, c] == wall
+            big[:, REF_ROWS - 1, c] = np.where(door, ord("."), big[:, REF_ROWS - 1, c])
+    if COLS > REF_COLS:
+        for r in range(3, REF_ROWS - 1, 7):
+            door = big[:, r, REF_COLS - 1] == wall
+            big[:, r, REF_COLS - 1] = np.where(door, ord("."), big[:, r, REF_COLS - 1])
+    big[:, 0, :] = np.where(np.isin(big[:, 0, :], list(b".O")), wall, big[:, 0, :])
+    big[:, :, 0] = np.where(np.isin(big[:, :, 0], list(b".O")), wall, big[:, :, 0])
+    big[:, ROWS - 1, :] = wall
+    big[:, :, COLS - 1] = wall
+    return big.reshape(-1), bigp.reshape(-1)
+
+
 def from_json(obj):
-    assert obj["format"] == "strikeforce_b200.arena/1" and obj["dims"] == [FLOORS, ROWS, COLS]
+    assert obj["format"] == "strikeforce_b200.arena/1" and obj["dims"] in ([FLOORS, ROWS, COLS], [FLOORS, REF_ROWS, REF_COLS])
     cells = _rle_decode([[ord(v), n] for v, n in obj["cells_rle"]], np.uint8)
+    portal = _rle_decode(obj["portal_rle"], np.int16)
+    if obj["dims"] != [FLOORS, ROWS, COLS]:
+        cells, portal = enlarge(cells, portal)
     data = ArenaData(
         map_cells=cells,
-        map_portal=_rle_decode(obj["portal_rle"], np.int16),
+        map_portal=portal,
         consumables=np.array(obj["consumables"], dtype=np.int32),
         throwables=np.array(obj["throwables"], dtype=np.int32),
         weapons=np.array(obj["weapons"], dtype=np.int32),

@@ -12,7 +12,7 @@ import subprocess
 from . import config as sfcfg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("SF_LIB_PATH") or os.path.join(_HERE, "libstrikeforce_b200.so")
+LIB_PATH = os.environ.get("SF_LIB_PATH") or os.path.join(_HERE, "libstrikeforce_b200%s.so" % sfcfg.GEOMETRY_TAG)
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 EXPORTS = [

@@ -15,7 +15,7 @@ from strikeforce_b200 import config as sfcfg  # noqa: E402
 
 # extra compiler flags build a variant next to the default one (e.g. "-DSF_BT_SLOTS=7 -DSF_BT_FULL=5": a
 # bullet-flag table so small that most flags spill into the overlay); HOSTCHECK_CFLAGS sets the default variant
-EXTRA = tuple(os.environ.get("HOSTCHECK_CFLAGS", "").split())
+EXTRA = tuple(os.environ.get("HOSTCHECK_CFLAGS", "").split()) + tuple(sfcfg.GEOMETRY_CFLAGS)
 _libs = {}
 
 

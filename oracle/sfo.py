@@ -194,7 +194,7 @@ def diff_records(a, b, limit=10):
             kind, index = key
             extra = ""
             if kind == 7:
-                extra = " (f,r,c)=(%d,%d,%d)" % (index // 3000, index // 100 % 30, index % 100)
+                extra = " (f,r,c)=(%d,%d,%d)" % (index // (sfcfg.ROWS * sfcfg.COLS), index // sfcfg.COLS % sfcfg.ROWS, index % sfcfg.COLS)
             msgs.append("%s[%d]%s: %s != %s" % (names.get(kind, kind), index, extra, pa.get(key), pb.get(key)))
             if len(msgs) >= limit:
                 break

@@ -42,6 +42,24 @@ def oracles_for(arena, mode, n, base, teams, max_steps):
     return out
 
 
+def beyond_reference(o):
+    """humans, zombies, bullets and dynamic cells of an oracle arena that lie outside the reference's 30 x 100"""
+    n = 0
+    for (kind, index), f in sfo.parse_record(o.dump()).items():
+        if kind == 3 and f[0]:
+            r, c = f[5], f[6]
+        elif kind == 4:
+            r, c = f[2], f[3]
+        elif kind == 5:
+            r, c = f[1], f[2]
+        elif kind == 7:
+            r, c = index // sfcfg.COLS % sfcfg.ROWS, index % sfcfg.COLS
+        else:
+            continue
+        n += r >= sfdata.REF_ROWS or c >= sfdata.REF_COLS
+    return n
+
+
 def run_host(arena):
     import hostcheck
     for name, mode, n, steps, agents, teams in CASES:
@@ -61,7 +79,10 @@ def run_host(arena):
                     episode[e] += 1
                     o.reset(lvl, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
                 assert np.uint64(hs.state_hash(e)) == np.uint64(o.state_hash()), "%s: state, step %d arena %d" % (name, t, e)
-        print("host %s: %d arenas x %d steps on %dx%d, %d episodes: bit-exact" % (name, n, steps, sfcfg.ROWS, sfcfg.COLS, sum(episode)))
+        out = sum(beyond_reference(o) for o, _ in ora)
+        assert out > 0, "%s: nothing ever left the reference's 30 x 100" % name
+        print("host %s: %d arenas x %d steps on %dx%d, %d episodes: bit-exact (%d entities / dynamic cells outside the reference's "
+              "30x100 at the end)" % (name, n, steps, sfcfg.ROWS, sfcfg.COLS, sum(episode), out))
 
 
 def run_gpu(arena):
@@ -101,7 +122,10 @@ def run_gpu(arena):
                         episode[e] += 1
                         o.reset(lvl, common.synth_tb(base + e), common.synth_serial(base + e, episode[e]))
                     assert h[e] == np.uint64(o.state_hash()), "%s: state, step %d arena %d" % (name, t, e)
-            print("gpu %s: %d arenas x %d steps on %dx%d, %d episodes: bit-exact" % (name, n, steps, sfcfg.ROWS, sfcfg.COLS, sum(episode)))
+            out = sum(beyond_reference(o) for o, _ in ora)
+            assert out > 0, "%s: nothing ever left the reference's 30 x 100" % name
+            print("gpu %s: %d arenas x %d steps on %dx%d, %d episodes: bit-exact (%d entities / dynamic cells outside the "
+                  "reference's 30x100 at the end)" % (name, n, steps, sfcfg.ROWS, sfcfg.COLS, sum(episode), out))
         finally:
             sim.close()
 
